@@ -1,0 +1,518 @@
+// C ABI of sslap_b200 (see include/sslap_b200.h).  Host-side orchestration only: staging, CSR build, the
+// Hopcroft-Karp phase loop, one cooperative launch of the persistent auction kernel, and the meta read-back.
+#include "../../include/sslap_b200.h"
+#include "auction.cuh"
+#include "build.cuh"
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <chrono>
+
+// ---- kernels' launchers (csr_build.cu / auction.cu / hopcroft.cu)
+
+
+extern "C" {
+cudaError_t sslapb_launch_coo_ingest(const void *, const void *, int, long long, const double *, long long, int, int, int,
+                                     int *, double *, long long *, SslapbBuildFlags *, int, cudaStream_t);
+cudaError_t sslapb_launch_index_max(const void *, const void *, int, long long, long long, long long *, int, cudaStream_t);
+cudaError_t sslapb_launch_dense_count(const double *, int, int, long long *, SslapbBuildFlags *, int, cudaStream_t);
+cudaError_t sslapb_launch_dense_fill(const double *, int, int, int, const long long *, int *, double *,
+                                     SslapbBuildFlags *, int, cudaStream_t);
+cudaError_t sslapb_launch_auction(const SslapbAuctionParams *, int, cudaStream_t);
+cudaError_t sslapb_auction_grid_size(int, int *);
+cudaError_t sslapb_launch_bid_sweep(const SslapbAuctionParams *, const int *, int, float, int, int, cudaStream_t);
+cudaError_t sslapb_hk_launch_greedy(const long long *, const int *, int, int *, int *, SslapbHkFlags *, int, cudaStream_t);
+cudaError_t sslapb_hk_launch_phase_init(int, int, const int *, int *, int *, SslapbHkFlags *, int, cudaStream_t);
+cudaError_t sslapb_hk_launch_bfs_level(const long long *, const int *, int, int, const int *, int *, SslapbHkFlags *, int,
+                                       cudaStream_t);
+cudaError_t sslapb_hk_launch_augment(const long long *, const int *, int, int, int *, int *, int *, int *, long long *,
+                                     int *, SslapbHkFlags *, int, cudaStream_t);
+}
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = (bytes + 255) & ~(size_t)255;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace
+
+struct sslapb_handle {
+    int device = 0;
+    int sms = 0;
+    int grid = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    std::string err;
+    int t_small = 32;
+    long long watchdog_ms = 600000;
+    // resident problem
+    int N = 0, M = 0;
+    long long nnz = 0;
+    bool has_vals = false;
+    DevBuf stage_idx, stage_val, stage_mat, cols, vals, rowptr, flags;
+    // auction state
+    DevBuf price, owner, p2o, list, mover, bidj, bidv, bidkey, winpos, hole_count, chosen, ctrl, bidders, flush;
+    // HK state
+    DevBuf pair_u, pair_v, dist, visited, cursor, pred, hkflags;
+};
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+            return -(int)e_;                                                                             \
+        }                                                                                                \
+    } while (0)
+
+static int fail(sslapb_handle *h, int code, const std::string &msg)
+{
+    if (h) h->err = msg;
+    return code;
+}
+
+extern "C" int sslapb_create(int device, sslapb_handle **out)
+{
+    if (!out) return SSLAPB_E_BAD_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return -(int)e;
+    if (device < 0 || device >= count) return SSLAPB_E_BAD_ARG;
+    sslapb_handle *h = new sslapb_handle();
+    h->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { delete h; return -(int)e; }
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device);
+    if (!coop) { delete h; return SSLAPB_E_BAD_ARG; }
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete h; return -(int)e; }
+    for (auto &ev : h->ev) cudaEventCreate(&ev);
+    if ((e = sslapb_auction_grid_size(device, &h->grid)) != cudaSuccess) { delete h; return -(int)e; }
+    *out = h;
+    return SSLAPB_OK;
+}
+
+extern "C" void sslapb_destroy(sslapb_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf *all[] = {&h->stage_idx, &h->stage_val, &h->stage_mat, &h->cols, &h->vals, &h->rowptr, &h->flags, &h->price,
+                     &h->owner, &h->p2o, &h->list, &h->mover, &h->bidj, &h->bidv, &h->bidkey, &h->winpos,
+                     &h->hole_count, &h->chosen, &h->ctrl, &h->bidders, &h->flush, &h->pair_u, &h->pair_v, &h->dist,
+                     &h->visited, &h->cursor, &h->pred, &h->hkflags};
+    for (DevBuf *b : all) b->release();
+    for (auto &ev : h->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" const char *sslapb_last_error(const sslapb_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+extern "C" int sslapb_set_option(sslapb_handle *h, const char *name, int64_t value)
+{
+    if (!h || !name) return SSLAPB_E_BAD_ARG;
+    if (!strcmp(name, "t_small")) { if (value < 0 || value > 32) return SSLAPB_E_BAD_ARG; h->t_small = (int)value; return 0; }
+    if (!strcmp(name, "watchdog_ms")) { if (value <= 0) return SSLAPB_E_BAD_ARG; h->watchdog_ms = value; return 0; }
+    return fail(h, SSLAPB_E_BAD_ARG, std::string("unknown option ") + name);
+}
+
+extern "C" void *sslapb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void sslapb_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ----------------------------------------------------------------------------------------------------------------------
+// CSR build
+// ----------------------------------------------------------------------------------------------------------------------
+static int build_from_coo(sslapb_handle *h, const void *rows, const void *cols, int idx_bytes, int64_t stride,
+                          const double *val, int64_t nnz, int32_t &n_rows, int32_t &n_cols, int negate, int mem,
+                          SslapbBuildFlags &F)
+{
+    if (!rows || !cols || nnz < 0 || (idx_bytes != 4 && idx_bytes != 8)) return fail(h, SSLAPB_E_BAD_ARG, "bad COO arguments");
+    const bool interleaved = stride == 2 && (const char *)cols == (const char *)rows + idx_bytes;
+    if (!(interleaved || stride == 1)) return fail(h, SSLAPB_E_BAD_ARG, "COO must be an interleaved (K,2) array or two contiguous arrays");
+    if (nnz >= (1ll << 40)) return fail(h, SSLAPB_E_BAD_ARG, "nnz too large");
+    const void *d_rows = rows, *d_cols = cols;
+    const double *d_val = val;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    if (!(mem & SSLAPB_MEM_DEVICE_IN) && nnz > 0) {
+        const size_t ib = (size_t)idx_bytes;
+        CK(h->stage_idx.reserve(2 * (size_t)nnz * ib));
+        char *s = h->stage_idx.as<char>();
+        if (interleaved) {
+            CK(cudaMemcpyAsync(s, rows, 2 * (size_t)nnz * ib, cudaMemcpyHostToDevice, h->stream));
+            d_rows = s; d_cols = s + ib;
+        } else {
+            CK(cudaMemcpyAsync(s, rows, (size_t)nnz * ib, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(s + (size_t)nnz * ib, cols, (size_t)nnz * ib, cudaMemcpyHostToDevice, h->stream));
+            d_rows = s; d_cols = s + (size_t)nnz * ib;
+        }
+        if (val) {
+            CK(h->stage_val.reserve((size_t)nnz * sizeof(double)));
+            CK(cudaMemcpyAsync(h->stage_val.p, val, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            d_val = h->stage_val.as<double>();
+        }
+    }
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(h->flags.reserve(sizeof(SslapbBuildFlags) + 2 * sizeof(long long)));
+    CK(cudaMemsetAsync(h->flags.p, 0, sizeof(SslapbBuildFlags) + 2 * sizeof(long long), h->stream));
+    if ((n_rows <= 0 || n_cols <= 0) && nnz > 0) {          // AuctionSolver.__init__ infers max+1 (auction_.pyx:209-210)
+        long long *mx = reinterpret_cast<long long *>(h->flags.as<char>() + sizeof(SslapbBuildFlags));
+        CK(sslapb_launch_index_max(d_rows, d_cols, idx_bytes, stride, nnz, mx, h->sms, h->stream));
+        long long hm[2];
+        CK(cudaMemcpyAsync(hm, mx, sizeof hm, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (hm[0] < 0 || hm[1] < 0 || hm[0] >= 0x7fffffff || hm[1] >= 0x7fffffff)
+            return fail(h, SSLAPB_E_OUT_OF_RANGE, "negative or oversized index in loc");
+        if (n_rows <= 0) n_rows = (int32_t)hm[0] + 1;
+        if (n_cols <= 0) n_cols = (int32_t)hm[1] + 1;
+    }
+    if (n_rows <= 0 || n_cols <= 0) return fail(h, SSLAPB_E_BAD_ARG, "empty problem");
+    CK(h->cols.reserve(((size_t)nnz + 8) * sizeof(int)));
+    CK(h->rowptr.reserve(((size_t)n_rows + 2) * sizeof(long long)));
+    CK(cudaMemsetAsync(h->cols.as<int>() + nnz, 0, 8 * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->rowptr.p, 0, ((size_t)n_rows + 2) * sizeof(long long), h->stream));
+    if (val) {
+        CK(h->vals.reserve(((size_t)nnz + 8) * sizeof(double)));
+        CK(cudaMemsetAsync(h->vals.as<double>() + nnz, 0, 8 * sizeof(double), h->stream));
+    }
+    CK(sslapb_launch_coo_ingest(d_rows, d_cols, idx_bytes, stride, d_val, nnz, n_rows, n_cols, negate, h->cols.as<int>(),
+                                val ? h->vals.as<double>() : nullptr, h->rowptr.as<long long>(),
+                                h->flags.as<SslapbBuildFlags>(), h->sms, h->stream));
+    CK(cudaMemcpyAsync(&F, h->flags.p, sizeof F, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (nnz == 0) F.empty_rows = 1;
+    h->N = n_rows; h->M = n_cols; h->nnz = nnz; h->has_vals = val != nullptr;
+    if (F.out_of_range) return fail(h, SSLAPB_E_OUT_OF_RANGE, "loc holds an index outside the matrix");
+    if (F.unsorted) return fail(h, SSLAPB_E_UNSORTED, "loc must be sorted by row (the reference's precondition, auction_.pyx:33-48)");
+    return SSLAPB_OK;
+}
+
+static int build_from_dense(sslapb_handle *h, const double *mat, int32_t n_rows, int32_t n_cols, int negate, int mem,
+                            bool want_vals, SslapbBuildFlags &F)
+{
+    if (!mat || n_rows <= 0 || n_cols <= 0) return fail(h, SSLAPB_E_BAD_ARG, "bad dense arguments");
+    const double *d_mat = mat;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    if (!(mem & SSLAPB_MEM_DEVICE_IN)) {
+        const size_t bytes = (size_t)n_rows * (size_t)n_cols * sizeof(double);
+        CK(h->stage_mat.reserve(bytes));
+        CK(cudaMemcpyAsync(h->stage_mat.p, mat, bytes, cudaMemcpyHostToDevice, h->stream));
+        d_mat = h->stage_mat.as<double>();
+    }
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(h->flags.reserve(sizeof(SslapbBuildFlags) + 2 * sizeof(long long)));
+    CK(cudaMemsetAsync(h->flags.p, 0, sizeof(SslapbBuildFlags), h->stream));
+    CK(h->rowptr.reserve(((size_t)n_rows + 2) * sizeof(long long)));
+    CK(sslapb_launch_dense_count(d_mat, n_rows, n_cols, h->rowptr.as<long long>(), h->flags.as<SslapbBuildFlags>(), h->sms,
+                                 h->stream));
+    CK(cudaMemcpyAsync(&F, h->flags.p, sizeof F, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const long long nnz = F.nnz;
+    CK(h->cols.reserve(((size_t)nnz + 8) * sizeof(int)));
+    CK(cudaMemsetAsync(h->cols.as<int>() + nnz, 0, 8 * sizeof(int), h->stream));
+    if (want_vals) {
+        CK(h->vals.reserve(((size_t)nnz + 8) * sizeof(double)));
+        CK(cudaMemsetAsync(h->vals.as<double>() + nnz, 0, 8 * sizeof(double), h->stream));
+    }
+    CK(sslapb_launch_dense_fill(d_mat, n_rows, n_cols, negate, h->rowptr.as<long long>(), h->cols.as<int>(),
+                                want_vals ? h->vals.as<double>() : nullptr, h->flags.as<SslapbBuildFlags>(), h->sms,
+                                h->stream));
+    CK(cudaMemcpyAsync(&F, h->flags.p, sizeof F, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->N = n_rows; h->M = n_cols; h->nnz = nnz; h->has_vals = want_vals;
+    return SSLAPB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Hopcroft-Karp phase loop on the resident CSR (feasibility_.pyx:199-211)
+// ----------------------------------------------------------------------------------------------------------------------
+static int run_hopcroft(sslapb_handle *h, int32_t *card_out)
+{
+    const int N = h->N, M = h->M;
+    CK(h->pair_u.reserve((size_t)N * 4)); CK(h->pair_v.reserve((size_t)M * 4));
+    CK(h->dist.reserve((size_t)N * 4)); CK(h->visited.reserve((size_t)M * 4));
+    CK(h->cursor.reserve((size_t)N * 8)); CK(h->pred.reserve((size_t)N * 4));
+    CK(h->hkflags.reserve(sizeof(SslapbHkFlags)));
+    const long long *rowptr = h->rowptr.as<long long>();
+    const int *cols = h->cols.as<int>();
+    SslapbHkFlags *dF = h->hkflags.as<SslapbHkFlags>();
+    CK(cudaMemsetAsync(h->pair_u.p, 0xff, (size_t)N * 4, h->stream));
+    CK(cudaMemsetAsync(h->pair_v.p, 0xff, (size_t)M * 4, h->stream));
+    CK(cudaMemsetAsync(dF, 0, sizeof(SslapbHkFlags), h->stream));
+    CK(sslapb_hk_launch_greedy(rowptr, cols, N, h->pair_u.as<int>(), h->pair_v.as<int>(), dF, h->sms, h->stream));
+    SslapbHkFlags F;
+    CK(cudaMemcpyAsync(&F, dF, sizeof F, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    long long matching = F.matched;
+    const long long bound = N < M ? N : M;
+    while (matching < bound) {
+        CK(sslapb_hk_launch_phase_init(N, M, h->pair_u.as<int>(), h->dist.as<int>(), h->visited.as<int>(), dF, h->sms, h->stream));
+        int level = 0, dist_nil = -1;
+        for (;;) {
+            CK(cudaMemsetAsync(&dF->grew, 0, sizeof(int), h->stream));
+            CK(sslapb_hk_launch_bfs_level(rowptr, cols, N, level, h->pair_v.as<int>(), h->dist.as<int>(), dF, h->sms, h->stream));
+            CK(cudaMemcpyAsync(&F, dF, sizeof F, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            if (F.found) { dist_nil = level + 1; break; }
+            if (!F.grew) break;
+            ++level;
+        }
+        if (dist_nil < 0) break;                              // no augmenting path: maximum (feasibility_.pyx:202-203)
+        CK(sslapb_hk_launch_augment(rowptr, cols, N, dist_nil, h->pair_u.as<int>(), h->pair_v.as<int>(), h->dist.as<int>(),
+                                    h->visited.as<int>(), h->cursor.as<long long>(), h->pred.as<int>(), dF, h->sms, h->stream));
+        CK(cudaMemcpyAsync(&F, dF, sizeof F, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (F.augmented <= 0) return fail(h, SSLAPB_E_ABORTED, "Hopcroft-Karp phase made no progress (internal error)");
+        matching += F.augmented;
+    }
+    *card_out = (int32_t)matching;
+    return SSLAPB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Auction on the resident CSR
+// ----------------------------------------------------------------------------------------------------------------------
+static int reserve_auction_state(sslapb_handle *h, SslapbAuctionParams &P)
+{
+    const size_t N = (size_t)h->N, M = (size_t)h->M;
+    CK(h->price.reserve(M * 8)); CK(h->owner.reserve(M * 4)); CK(h->p2o.reserve(N * 4));
+    CK(h->list.reserve(N * 4)); CK(h->mover.reserve(N * 4)); CK(h->bidj.reserve(N * 4)); CK(h->bidv.reserve(N * 8));
+    CK(h->bidkey.reserve(M * 8)); CK(h->winpos.reserve(M * 4)); CK(h->hole_count.reserve((size_t)h->grid * 4 + 64));
+    CK(h->chosen.reserve(N * 8)); CK(h->ctrl.reserve(sizeof(SslapbCtrl)));
+    P.N = h->N; P.M = h->M;
+    P.rowptr = h->rowptr.as<long long>(); P.cols = h->cols.as<int>(); P.vals = h->vals.as<double>();
+    P.price = h->price.as<double>(); P.owner = h->owner.as<int>(); P.p2o = h->p2o.as<int>();
+    P.list = h->list.as<int>(); P.mover = h->mover.as<int>(); P.bidj = h->bidj.as<int>(); P.bidv = h->bidv.as<double>();
+    P.bidkey = h->bidkey.as<unsigned long long>(); P.winpos = h->winpos.as<int>();
+    P.hole_count = h->hole_count.as<int>(); P.chosen = h->chosen.as<double>(); P.ctrl = h->ctrl.as<SslapbCtrl>();
+    P.t_small = h->t_small;
+    P.watchdog_ns = (unsigned long long)h->watchdog_ms * 1000000ull;
+    return SSLAPB_OK;
+}
+
+static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize, float eps_start, int64_t max_iter,
+                       int mem, int32_t *sol_out, sslapb_meta *meta)
+{
+    SslapbAuctionParams P;
+    int rc = reserve_auction_state(h, P);
+    if (rc) return rc;
+    const int N = h->N;
+    // eps schedule constants, auction_.pyx:242-252 (float32 arithmetic as in the generated C)
+    double cmax;
+    memcpy(&cmax, &F.maxabs, sizeof cmax);
+    const float C = (float)cmax;
+    float eps = (float)((double)C / 2.0);
+    const float target = (float)(1.0 / (double)N);
+    if (eps_start > 0) eps = eps_start;
+    SslapbCtrl c;
+    memset(&c, 0, sizeof c);
+    c.nu = N; c.eps = eps; c.target_eps = target; c.theta = 0.15f; c.max_iter = max_iter; c.ece_final = -1;
+    CK(cudaMemcpyAsync(P.ctrl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    CK(sslapb_launch_auction(&P, h->grid, h->stream));
+    CK(cudaEventRecord(h->ev[4], h->stream));
+    std::vector<double> chosen((size_t)N);
+    std::vector<int32_t> sol_tmp;
+    int32_t *sol_host = sol_out;
+    if (mem & SSLAPB_MEM_DEVICE_OUT) {
+        CK(cudaMemcpyAsync(sol_out, P.p2o, (size_t)N * 4, cudaMemcpyDeviceToDevice, h->stream));
+        sol_tmp.resize((size_t)N);
+        sol_host = sol_tmp.data();
+    }
+    CK(cudaMemcpyAsync(sol_host, P.p2o, (size_t)N * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(chosen.data(), P.chosen, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&c, P.ctrl, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (c.abort_flag) return fail(h, SSLAPB_E_ABORTED, c.abort_flag == 2 ? "empty row reached the bidding kernel" : "device watchdog fired");
+    double obj = 0.0;                                          // get_obj, auction_.pyx:489-523 (row order, double)
+    long long assigned = 0;
+    for (int i = 0; i < N; ++i) {
+        if (sol_host[i] == -1) continue;
+        ++assigned;
+        if (maximize) obj += chosen[(size_t)i]; else obj -= chosen[(size_t)i];
+    }
+    if (meta) {
+        meta->start_eps = eps; meta->final_eps = c.eps; meta->target_eps = target;
+        meta->eCE = c.ece_final > 0; meta->soln_found = (c.nu == 0) && (c.ece_final > 0);
+        meta->its = c.its; meta->nreductions = c.nreductions; meta->n_assigned = (int64_t)N - c.nu;
+        meta->obj64 = obj; meta->obj = (float)obj;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); meta->setup_ms = ms;
+        cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); meta->solve_ms = ms;
+        cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); meta->h2d_ms = ms;
+        meta->n_rows = h->N; meta->n_cols = h->M; meta->nnz = h->nnz;
+        meta->rounds_grid = c.rounds_grid; meta->rounds_warp = c.rounds_warp; meta->rounds_solo = c.rounds_solo;
+        meta->stop_reason = c.done;
+        (void)assigned;
+    }
+    return SSLAPB_OK;
+}
+
+static int solve_resident(sslapb_handle *h, const SslapbBuildFlags &F, int maximize, float eps_start, int64_t max_iter,
+                          int cardinality_check, int mem, int32_t *sol_out, sslapb_meta *meta)
+{
+    if (meta) { memset(meta, 0, sizeof *meta); meta->cardinality = -1; meta->n_rows = h->N; meta->n_cols = h->M; meta->nnz = h->nnz; }
+    if (h->nnz < h->N)                                         // auction_.pyx:559-560 / :604-605
+        return fail(h, SSLAPB_E_FEWER_THAN_N, "fewer valid values than rows");
+    if (cardinality_check) {                                   // :562-566 / :608-612
+        auto t0 = std::chrono::steady_clock::now();
+        int32_t card = 0;
+        int rc = run_hopcroft(h, &card);
+        if (rc) return rc;
+        if (meta) {
+            meta->cardinality = card;
+            meta->hk_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
+        if (card < h->N) return fail(h, SSLAPB_E_CARDINALITY, "maximum matching smaller than the number of rows");
+    } else if (F.empty_rows) {
+        return fail(h, SSLAPB_E_EMPTY_ROW, "a row has no valid entry");
+    }
+    if (!sol_out) return fail(h, SSLAPB_E_BAD_ARG, "sol_out is NULL");
+    const float hk_ms = meta ? meta->hk_ms : 0.f;
+    const int32_t card = meta ? meta->cardinality : -1;
+    int rc = run_auction(h, F, maximize, eps_start, max_iter, mem, sol_out, meta);
+    if (meta) { meta->hk_ms = hk_ms; meta->cardinality = card; }
+    return rc;
+}
+
+extern "C" int sslapb_auction_coo(sslapb_handle *h, const void *rows, const void *cols, int idx_bytes, int64_t stride,
+                                  const double *val, int64_t nnz, int32_t n_rows, int32_t n_cols, int maximize,
+                                  float eps_start, int64_t max_iter, int cardinality_check, int mem, int32_t *sol_out,
+                                  sslapb_meta *meta)
+{
+    if (!h) return SSLAPB_E_BAD_ARG;
+    if (!val) return fail(h, SSLAPB_E_BAD_ARG, "val is NULL");
+    CK(cudaSetDevice(h->device));
+    SslapbBuildFlags F;
+    memset(&F, 0, sizeof F);
+    if (nnz == 0) return fail(h, SSLAPB_E_FEWER_THAN_N, "no entries");
+    int rc = build_from_coo(h, rows, cols, idx_bytes, stride, val, nnz, n_rows, n_cols, !maximize, mem, F);
+    if (rc) return rc;
+    return solve_resident(h, F, maximize, eps_start, max_iter, cardinality_check, mem, sol_out, meta);
+}
+
+extern "C" int sslapb_auction_dense(sslapb_handle *h, const double *mat, int32_t n_rows, int32_t n_cols, int maximize,
+                                    float eps_start, int64_t max_iter, int cardinality_check, int mem, int32_t *sol_out,
+                                    sslapb_meta *meta)
+{
+    if (!h) return SSLAPB_E_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    SslapbBuildFlags F;
+    memset(&F, 0, sizeof F);
+    int rc = build_from_dense(h, mat, n_rows, n_cols, !maximize, mem, true, F);
+    if (rc) return rc;
+    return solve_resident(h, F, maximize, eps_start, max_iter, cardinality_check, mem, sol_out, meta);
+}
+
+static int hopcroft_finish(sslapb_handle *h, int mem, int32_t *left_out, int32_t *right_out, int32_t *size_out)
+{
+    int32_t card = 0;
+    int rc = run_hopcroft(h, &card);
+    if (rc) return rc;
+    const cudaMemcpyKind kind = (mem & SSLAPB_MEM_DEVICE_OUT) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (left_out) CK(cudaMemcpyAsync(left_out, h->pair_u.p, (size_t)h->N * 4, kind, h->stream));
+    if (right_out) CK(cudaMemcpyAsync(right_out, h->pair_v.p, (size_t)h->M * 4, kind, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (size_out) *size_out = card;
+    return SSLAPB_OK;
+}
+
+extern "C" int sslapb_hopcroft_coo(sslapb_handle *h, const void *rows, const void *cols, int idx_bytes, int64_t stride,
+                                   int64_t nnz, int32_t n_rows, int32_t n_cols, int mem, int32_t *left_out,
+                                   int32_t *right_out, int32_t *size_out)
+{
+    if (!h) return SSLAPB_E_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    SslapbBuildFlags F;
+    memset(&F, 0, sizeof F);
+    int rc = build_from_coo(h, rows, cols, idx_bytes, stride, nullptr, nnz, n_rows, n_cols, 0, mem, F);
+    if (rc) return rc;
+    return hopcroft_finish(h, mem, left_out, right_out, size_out);
+}
+
+extern "C" int sslapb_hopcroft_dense(sslapb_handle *h, const double *mat, int32_t n_rows, int32_t n_cols, int mem,
+                                     int32_t *left_out, int32_t *right_out, int32_t *size_out)
+{
+    if (!h) return SSLAPB_E_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    SslapbBuildFlags F;
+    memset(&F, 0, sizeof F);
+    int rc = build_from_dense(h, mat, n_rows, n_cols, 0, mem, false, F);
+    if (rc) return rc;
+    return hopcroft_finish(h, mem, left_out, right_out, size_out);
+}
+
+extern "C" int sslapb_get_prices(sslapb_handle *h, double *prices_out)
+{
+    if (!h || !prices_out || !h->price.p || h->M <= 0) return SSLAPB_E_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(prices_out, h->price.p, (size_t)h->M * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return SSLAPB_OK;
+}
+
+extern "C" int sslapb_bid_sweep(sslapb_handle *h, const double *prices, const int32_t *bidders, int32_t nb, float eps,
+                                int merge, int iters, int flush_l2, int32_t *jbest_out, double *bid_out,
+                                float *avg_ms_out)
+{
+    if (!h || h->N <= 0 || !h->has_vals || nb <= 0 || iters < 1) return fail(h, SSLAPB_E_BAD_ARG, "no resident problem / bad arguments");
+    if (!bidders && nb > h->N) return fail(h, SSLAPB_E_BAD_ARG, "nb > N");
+    CK(cudaSetDevice(h->device));
+    SslapbAuctionParams P;
+    const bool fresh = h->price.cap < (size_t)h->M * 8;
+    int rc = reserve_auction_state(h, P);
+    if (rc) return rc;
+    if (prices) CK(cudaMemcpyAsync(P.price, prices, (size_t)h->M * 8, cudaMemcpyHostToDevice, h->stream));
+    else if (fresh) CK(cudaMemsetAsync(P.price, 0, (size_t)h->M * 8, h->stream));
+    const int *d_bidders = nullptr;
+    if (bidders) {
+        CK(h->bidders.reserve((size_t)nb * 4));
+        CK(cudaMemcpyAsync(h->bidders.p, bidders, (size_t)nb * 4, cudaMemcpyHostToDevice, h->stream));
+        d_bidders = h->bidders.as<int>();
+        if ((size_t)nb > (size_t)h->N) { CK(h->bidj.reserve((size_t)nb * 4)); CK(h->bidv.reserve((size_t)nb * 8)); P.bidj = h->bidj.as<int>(); P.bidv = h->bidv.as<double>(); }
+    }
+    const size_t flush_bytes = (size_t)256 << 20;
+    if (flush_l2) CK(h->flush.reserve(flush_bytes));
+    float total = 0.f;
+    for (int it = 0; it < iters; ++it) {
+        if (merge) CK(cudaMemsetAsync(P.bidkey, 0, (size_t)h->M * 8, h->stream));
+        if (flush_l2) CK(cudaMemsetAsync(h->flush.p, it & 0xff, flush_bytes, h->stream));
+        CK(cudaEventRecord(h->ev[3], h->stream));
+        CK(sslapb_launch_bid_sweep(&P, d_bidders, nb, eps, merge, h->grid, h->stream));
+        CK(cudaEventRecord(h->ev[4], h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]));
+        total += ms;
+    }
+    if (merge) CK(cudaMemsetAsync(P.bidkey, 0, (size_t)h->M * 8, h->stream));
+    if (jbest_out) CK(cudaMemcpyAsync(jbest_out, P.bidj, (size_t)nb * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (bid_out) CK(cudaMemcpyAsync(bid_out, P.bidv, (size_t)nb * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (avg_ms_out) *avg_ms_out = total / (float)iters;
+    return SSLAPB_OK;
+}

@@ -1,0 +1,44 @@
+// Device-side state of one auction solve (sslap_b200).  Host code lives in api.cu; kernels in auction.cu.
+#pragma once
+#include "common.cuh"
+
+// Control block in device memory: the only cross-CTA communication channel of the persistent kernel.
+struct SslapbCtrl {
+    unsigned bar_count;       // grid barrier: arrivals
+    unsigned bar_gen;         // grid barrier: generation
+    int abort_flag;           // set by the watchdog (a barrier waited longer than watchdog_ns) or an internal assert
+    int nu;                   // number of unassigned persons (auction_.pyx:198 num_unassigned)
+    int done;                 // 0 running | 1 target-eps CS holds (:275,309) | 2 eps < target (:280) | 3 max_iter (:309)
+    float eps;                // current eps, float32 as in the reference (:180)
+    float target_eps;         // float32(1/N) (:247)
+    float theta;              // 0.15f (:248)
+    long long its;            // nits (:273)
+    long long max_iter;
+    int nreductions;          // :292
+    int ece_viol;             // set by the eCE sweep when some person violates eps-CS
+    int tie_flag;             // some atomicMax saw an equal bid this round -> run the position tie-break pass
+    int ece_final;            // meta['eCE'] (:297); -1 until known
+    long long rounds_grid, rounds_warp, rounds_solo;   // instrumentation: rounds executed per regime
+    unsigned long long t_begin, t_end;                 // %globaltimer at kernel start / end
+};
+
+struct SslapbAuctionParams {
+    int N, M;
+    const long long *rowptr;  // N+1 row start offsets (i_starts_stops, auction_.pyx:223)
+    const int *cols;          // flat_j (:229); 16-byte aligned base, >= 4 entries of slack after nnz
+    const double *vals;       // sign-folded values ('min' negated, :236-237); same alignment/slack
+    double *price;            // p (:220)
+    int *owner;               // object_to_person (:232)
+    int *p2o;                 // person_to_object (:231)
+    int *list;                // unassigned_people (:260), positions [0,nu)
+    int *mover;               // grid-mode compaction: k-th live entry right of the new count
+    int *bidj;                // per list position: object bid on   (objects_bidded, :324)
+    double *bidv;             // per list position: bid value       (bids, :325)
+    unsigned long long *bidkey;  // per object: order-preserving image of the best bid (best_bids, :255); 0 = none
+    int *winpos;              // per object: smallest list position among equal best bids (tie rule of :379)
+    int *hole_count;          // per CTA: holes produced in its chunk of positions
+    double *chosen;           // per person: sum of (folded) values of entries equal to its object (get_obj, :504-521)
+    SslapbCtrl *ctrl;
+    int t_small;              // nu <= t_small (<= 32) -> CTA 0 runs the round alone (warp-list regime)
+    unsigned long long watchdog_ns;
+};
