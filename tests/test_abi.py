@@ -1,0 +1,83 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/sslap_b200.h declares,
+and the Python front mirrors the reference's argument handling.  No compute calls (no GPU here)."""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+
+import sslap_b200
+from sslap_b200 import _native as nat
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sslap_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sslapb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(nat.LIB_PATH), "build the CUDA library first: make -C sslap_b200/csrc"
+    lib = ctypes.CDLL(nat.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/sslap_b200.h but not exported"
+    assert set(nat.EXPORTS) == set(syms)
+
+
+def test_meta_struct_layout_matches_header():
+    # field order/types of struct sslapb_meta as declared in the header
+    text = open(os.path.join(ROOT, "include", "sslap_b200.h")).read()
+    body = re.search(r"typedef struct sslapb_meta \{(.*?)\} sslapb_meta;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            names += [n.strip() for n in decl.split(None, 1)[1].split(",")]
+    assert names == [f[0] for f in nat.Meta._fields_]
+    assert ctypes.sizeof(nat.Meta) % 8 == 0
+
+
+def test_signatures_mirror_the_reference():
+    # /root/reference/sslap/auction_solve.py:6-8 and check_feasible.py:5
+    p = inspect.signature(sslap_b200.auction_solve).parameters
+    assert list(p)[:10] == ["mat", "loc", "val", "coo_mat", "problem", "eps_start", "max_iter", "fast", "size",
+                            "cardinality_check"]
+    assert (p["problem"].default, p["eps_start"].default, p["max_iter"].default, p["fast"].default,
+            p["size"].default, p["cardinality_check"].default) == ("min", 0.0, 1000000, False, None, True)
+    q = inspect.signature(sslap_b200.hopcroft_solve).parameters
+    assert list(q)[:3] == ["loc", "mat", "lookup"]
+
+
+def test_argument_errors_raise_before_touching_the_gpu(monkeypatch):
+    class FakeHandle:
+        ptr = None
+    monkeypatch.setattr(nat, "default_handle", lambda device=None: FakeHandle())
+    with pytest.raises(ValueError, match="One of the following formats is expected"):
+        sslap_b200.auction_solve()                                   # auction_solve.py:51-52
+    with pytest.raises(ValueError, match="Buffer dtype mismatch"):
+        sslap_b200.auction_solve(loc=np.zeros((3, 2), dtype=np.int32), val=np.ones(3, dtype=np.float32))
+    with pytest.raises(AssertionError, match="Exactly one of the arguments"):
+        sslap_b200.hopcroft_solve()                                   # feasibility_.pyx:232-233
+    with pytest.raises(AssertionError):
+        sslap_b200.hopcroft_solve(loc=np.zeros((1, 2), dtype=np.int32), mat=np.zeros((1, 1)))
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly instead of computing on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        nat.Handle(0)
+    src = ""
+    for f in os.listdir(os.path.join(ROOT, "sslap_b200")):
+        if f.endswith(".py"):
+            src += open(os.path.join(ROOT, "sslap_b200", f)).read()
+    assert "oracle" not in src.replace("cardinality oracle", ""), "the product package must not reference oracle/"
