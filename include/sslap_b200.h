@@ -62,6 +62,8 @@ typedef struct sslapb_meta {
     int32_t n_rows, n_cols;  /* N, M actually used (inferred as max+1 when passed <= 0, auction_.pyx:209-210) */
     int64_t nnz;
     int64_t rounds_grid, rounds_warp, rounds_solo;   /* rounds executed per regime */
+    float   prof_ms[8];      /* device time by section: grid bid, grid assign, grid compaction, warp regime, solo regime,
+                                eCE + phase change, (unused), grid barriers */
     int32_t stop_reason;     /* 1 target-eps CS holds (:275) | 2 eps < target (:280) | 3 max_iter (:309) */
     int32_t pad;
 } sslapb_meta;

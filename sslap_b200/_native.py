@@ -8,7 +8,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsslap_b200.so")
+LIB_PATH = os.environ.get("SSLAP_B200_LIB", os.path.join(_HERE, "csrc", "libsslap_b200.so"))
 
 OK, E_FEWER_THAN_N, E_CARDINALITY, E_UNSORTED, E_BAD_ARG, E_OUT_OF_RANGE, E_EMPTY_ROW, E_ABORTED = range(8)
 MEM_HOST, MEM_DEVICE_IN, MEM_DEVICE_OUT = 0, 1, 2
@@ -26,6 +26,7 @@ class Meta(C.Structure):
                 ("setup_ms", C.c_float), ("solve_ms", C.c_float), ("hk_ms", C.c_float), ("h2d_ms", C.c_float),
                 ("cardinality", C.c_int32), ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("nnz", C.c_int64),
                 ("rounds_grid", C.c_int64), ("rounds_warp", C.c_int64), ("rounds_solo", C.c_int64),
+                ("prof_ms", C.c_float * 8),
                 ("stop_reason", C.c_int32), ("pad", C.c_int32)]
 
 

@@ -4,6 +4,7 @@
 #include "auction.cuh"
 #include "build.cuh"
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <string>
@@ -299,13 +300,13 @@ static int run_hopcroft(sslapb_handle *h, int32_t *card_out)
 static int reserve_auction_state(sslapb_handle *h, SslapbAuctionParams &P)
 {
     const size_t N = (size_t)h->N, M = (size_t)h->M;
-    CK(h->price.reserve(M * 8)); CK(h->owner.reserve(M * 4)); CK(h->p2o.reserve(N * 4));
+    CK(h->price.reserve(M * 8)); CK(h->owner.reserve(M * sizeof(SslapbObjRec))); CK(h->p2o.reserve(N * 4));
     CK(h->list.reserve(N * 4)); CK(h->mover.reserve(N * 4)); CK(h->bidj.reserve(N * 4)); CK(h->bidv.reserve(N * 8));
     CK(h->bidkey.reserve(M * 8)); CK(h->winpos.reserve(M * 4)); CK(h->hole_count.reserve((size_t)h->grid * 4 + 64));
     CK(h->chosen.reserve(N * 8)); CK(h->ctrl.reserve(sizeof(SslapbCtrl)));
     P.N = h->N; P.M = h->M;
     P.rowptr = h->rowptr.as<long long>(); P.cols = h->cols.as<int>(); P.vals = h->vals.as<double>();
-    P.price = h->price.as<double>(); P.owner = h->owner.as<int>(); P.p2o = h->p2o.as<int>();
+    P.price = h->price.as<double>(); P.rec = h->owner.as<SslapbObjRec>(); P.p2o = h->p2o.as<int>();
     P.list = h->list.as<int>(); P.mover = h->mover.as<int>(); P.bidj = h->bidj.as<int>(); P.bidv = h->bidv.as<double>();
     P.bidkey = h->bidkey.as<unsigned long long>(); P.winpos = h->winpos.as<int>();
     P.hole_count = h->hole_count.as<int>(); P.chosen = h->chosen.as<double>(); P.ctrl = h->ctrl.as<SslapbCtrl>();
@@ -366,6 +367,8 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
         cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); meta->h2d_ms = ms;
         meta->n_rows = h->N; meta->n_cols = h->M; meta->nnz = h->nnz;
         meta->rounds_grid = c.rounds_grid; meta->rounds_warp = c.rounds_warp; meta->rounds_solo = c.rounds_solo;
+        for (int k = 0; k < 8; ++k) meta->prof_ms[k] = (float)((double)c.prof[k] * 1e-6);
+        if (getenv("SSLAPB_PRINT_PROF2")) { fprintf(stderr, "prof2:"); for (int k = 0; k < 8; ++k) fprintf(stderr, " %llu", c.prof2[k]); fprintf(stderr, "\n"); }
         meta->stop_reason = c.done;
         (void)assigned;
     }

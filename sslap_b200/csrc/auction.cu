@@ -17,7 +17,20 @@
 //   solo  (nu <= 4)     : warp 0 of CTA 0 only; 32/16/8 lanes per bidder; no block barrier at all.
 #include "auction.cuh"
 
-#define SOLO_MAX 4
+#ifdef SSLAPB_PROFILE_SOLO
+// Diagnostic build only: cycle stamps inside the single-bidder round (the stamp waits for `dep` through a control dependency).
+__device__ __forceinline__ long long sslapb_clk_after(int dep)
+{
+    if (dep == 0x7ffffff1) __trap();
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory");
+    return t;
+}
+#define SSLAPB_PROBE(K_, DEP_) do { if (acc) { const long long t_ = sslapb_clk_after((int)(DEP_)); acc[K_] += t_ - tprev; tprev = t_; } } while (0)
+#else
+#define SSLAPB_PROBE(K_, DEP_) do { } while (0)
+#endif
+#define SSLAPB_THREADS 512       // persistent kernel: one CTA of 16 warps per SM (128 registers per thread)
 
 // ----------------------------------------------------------------------------------------------------------------------
 // Row sweep: top-2 of (a_ij - p_j) over one CSR row by a group of W lanes (bidding loop, auction_.pyx:346-358).
@@ -25,61 +38,159 @@
 // double2 of values); entries of the chunk outside [start,end) belong to neighbouring rows and are masked.
 // Returns (in every lane of the group) the object and the bid (a_ibest - w_i + eps, :360); jbest = -1 for an empty row.
 // ----------------------------------------------------------------------------------------------------------------------
-#define SSLAPB_VISIT(M_, VAL_, PR_, COL_, IDX_)                                          \
-    if (M_) {                                                                            \
-        const double vi_ = (VAL_) - (PR_);                                               \
-        if (vi_ >= b) { s = b; b = vi_; bc = (VAL_); bi = (IDX_); bj = (COL_); }         \
-        else if (vi_ > s) s = vi_;                                                       \
+// Key of one candidate: order-preserving 64-bit image of v = a_ij - p_j (computed in float64 exactly as the reference
+// does).  All comparisons of the sweep then run on the integer pipe (FP64 compares are ~5x slower on the critical path).
+// -0.0 is folded into +0.0 first so that integer order reproduces the reference's floating-point ties; 0 = "no entry".
+__device__ __forceinline__ unsigned long long sslapb_vkey(double val, double p, bool m)
+{
+    long long bits = __double_as_longlong(val - p);
+    if ((bits << 1) == 0) bits = 0;
+    const unsigned long long k = (unsigned long long)(bits ^ ((bits >> 63) | (long long)0x8000000000000000ull));
+    return m ? k : 0ull;
+}
+__device__ __forceinline__ double sslapb_key2double(unsigned long long k)
+{
+    const long long b = (long long)k;
+    return __longlong_as_double(b ^ (((~b) >> 63) | (long long)0x8000000000000000ull));
+}
+
+// What a bidder knows after its sweep: the object, the bid and (warp-list regimes only) the record of the object's
+// current owner, fetched speculatively for every candidate so that no dependent load follows the reduction.
+struct SslapbBid {
+    int j;                    // object bid on (-1: empty row)
+    double bid;
+    int powner;               // current owner of j (-1 none)
+    int pdeg;                 // its row
+    long long pstart;
+};
+
+template <int W>
+__device__ __forceinline__ unsigned sslapb_group_mask()
+{
+    return (W == 32) ? SSLAPB_FULL : (((1u << (W & 31)) - 1u) << ((threadIdx.x & 31) & ~(W - 1)));
+}
+
+// The sweep.  REC = false: prices gathered from price[] (grid regime, 8 B per candidate).  REC = true: prices and owner
+// records gathered from the 32-byte object records (warp-list regimes).
+template <int W, bool REC>
+__device__ __forceinline__ SslapbBid row_bid_core(const int *__restrict__ cols, const double *__restrict__ vals,
+                                                  const double *price, const SslapbObjRec *rec, long long start,
+                                                  long long end, int t, double eps, long long *acc = nullptr)
+{
+#ifdef SSLAPB_PROFILE_SOLO
+    long long tprev = 0;
+    if (acc) tprev = sslapb_clk_after(t);
+#endif
+    const int4 *c4 = reinterpret_cast<const int4 *>(cols);
+    const double2 *v2 = reinterpret_cast<const double2 *>(vals);
+    unsigned long long b = 0ull, s = 0ull;          // best / second-best key of this lane (0 = none)
+    double bc = 0.0;                                // value a_ij of the best entry
+    int bi = -1, bj = -1;                           // its index inside the row / its column
+    int4 br = make_int4(0, 0, -1, 0);               // its object's record (REC)
+    // Warp-uniform trip count (the widest group decides) keeps the loop convergent.
+    const long long c0 = start >> 2, c1 = (end + 3) >> 2;
+    int trips = (int)((c1 - c0 + (W - 1)) / W);
+    trips = (W == 32) ? __shfl_sync(SSLAPB_FULL, trips, 0) : __reduce_max_sync(SSLAPB_FULL, trips);
+#pragma unroll 1
+    for (int it = 0; it < trips; ++it) {
+        const long long ch = c0 + (long long)it * W + t;
+        if (ch >= c1) continue;
+        const int4 cj = REC ? __ldg(c4 + ch) : sslapb_ldg_stream_i4(c4 + ch);
+        const double2 va = REC ? __ldg(v2 + 2 * ch) : sslapb_ldg_stream_d2(v2 + 2 * ch);
+        const double2 vb = REC ? __ldg(v2 + 2 * ch + 1) : sslapb_ldg_stream_d2(v2 + 2 * ch + 1);
+        const int lo = (int)(start - (ch << 2)), hi = (int)min(end - (ch << 2), 4ll);
+        const bool m0 = (0 >= lo) & (0 < hi), m1 = (1 >= lo) & (1 < hi), m2 = (2 >= lo) & (2 < hi), m3 = (3 >= lo) & (3 < hi);
+        SSLAPB_PROBE(0, cj.x ^ __double2hiint(va.x) ^ __double2hiint(vb.y));
+        double p0, p1, p2, p3;
+        int4 r0, r1, r2, r3;
+        if (REC) {
+            const int4 z = make_int4(0, 0, -1, 0);
+            r0 = m0 ? *reinterpret_cast<const int4 *>(rec + cj.x) : z;
+            r1 = m1 ? *reinterpret_cast<const int4 *>(rec + cj.y) : z;
+            r2 = m2 ? *reinterpret_cast<const int4 *>(rec + cj.z) : z;
+            r3 = m3 ? *reinterpret_cast<const int4 *>(rec + cj.w) : z;
+            p0 = m0 ? rec[cj.x].price : 0.0;
+            p1 = m1 ? rec[cj.y].price : 0.0;
+            p2 = m2 ? rec[cj.z].price : 0.0;
+            p3 = m3 ? rec[cj.w].price : 0.0;
+            SSLAPB_PROBE(1, r0.z ^ r1.z ^ r2.z ^ r3.z ^ __double2hiint(p0) ^ __double2hiint(p1) ^ __double2hiint(p2) ^ __double2hiint(p3));
+        } else {
+            p0 = m0 ? price[cj.x] : 0.0;
+            p1 = m1 ? price[cj.y] : 0.0;
+            p2 = m2 ? price[cj.z] : 0.0;
+            p3 = m3 ? price[cj.w] : 0.0;
+        }
+        // top-2 of the four candidates by a two-level tournament (later entry wins equal keys: last maximal, :351)
+        const unsigned long long k0 = sslapb_vkey(va.x, p0, m0), k1 = sslapb_vkey(va.y, p1, m1);
+        const unsigned long long k2 = sslapb_vkey(vb.x, p2, m2), k3 = sslapb_vkey(vb.y, p3, m3);
+        const bool w01 = k1 >= k0, w23 = k3 >= k2;
+        const unsigned long long b01 = w01 ? k1 : k0, l01 = w01 ? k0 : k1;
+        const unsigned long long b23 = w23 ? k3 : k2, l23 = w23 ? k2 : k3;
+        const bool wf = b23 >= b01;
+        const unsigned long long b4 = wf ? b23 : b01;
+        const unsigned long long s4 = wf ? (b01 > l23 ? b01 : l23) : (b23 > l01 ? b23 : l01);
+        const int w4 = wf ? (w23 ? 3 : 2) : (w01 ? 1 : 0);
+        if (b4 >= b && b4 != 0ull) {                 // this chunk holds later entries: it wins equal keys
+            s = b > s4 ? b : s4;
+            b = b4;
+            bi = (int)((ch << 2) - start) + w4;
+            bc = (w4 & 2) ? ((w4 & 1) ? vb.y : vb.x) : ((w4 & 1) ? va.y : va.x);
+            bj = (w4 & 2) ? ((w4 & 1) ? cj.w : cj.z) : ((w4 & 1) ? cj.y : cj.x);
+            if (REC) br = (w4 & 2) ? ((w4 & 1) ? r3 : r2) : ((w4 & 1) ? r1 : r0);
+        } else {
+            s = b4 > s ? b4 : s;
+        }
+        SSLAPB_PROBE(2, bi ^ (int)b ^ (int)s);
     }
+    // cross-lane: lexicographic max of (key, row index) and the second-largest key, on the redux unit
+    const unsigned gm = sslapb_group_mask<W>();
+    const unsigned bh = (unsigned)(b >> 32), bl = (unsigned)b;
+    const unsigned hi = __reduce_max_sync(gm, bh);
+    const unsigned lo = __reduce_max_sync(gm, bh == hi ? bl : 0u);
+    const bool top = (bh == hi) & (bl == lo);
+    const int widx = __reduce_max_sync(gm, top ? bi : -1);
+    const bool iswin = top & (bi == widx) & (bi >= 0);
+    const unsigned long long cand = iswin ? s : b;
+    const unsigned chh = (unsigned)(cand >> 32), chl = (unsigned)cand;
+    const unsigned shi = __reduce_max_sync(gm, chh);
+    const unsigned slo = __reduce_max_sync(gm, chh == shi ? chl : 0u);
+    const unsigned long long skey = ((unsigned long long)shi << 32) | slo;
+    const unsigned own = __ballot_sync(SSLAPB_FULL, iswin) & gm;
+    const int src = own ? (__ffs(own) - 1) : (threadIdx.x & 31);
+    bc = __shfl_sync(SSLAPB_FULL, bc, src);
+    bj = __shfl_sync(SSLAPB_FULL, bj, src);
+    SslapbBid o;
+    o.j = own ? bj : -1;
+    if (REC) {
+        const int sx = __shfl_sync(SSLAPB_FULL, br.x, src), sy = __shfl_sync(SSLAPB_FULL, br.y, src);
+        o.powner = __shfl_sync(SSLAPB_FULL, br.z, src);
+        o.pdeg = __shfl_sync(SSLAPB_FULL, br.w, src);
+        o.pstart = (long long)(((unsigned long long)(unsigned)sy << 32) | (unsigned)sx);
+    } else {
+        o.powner = -1; o.pdeg = 0; o.pstart = 0;
+    }
+    const double wi = skey ? sslapb_key2double(skey) : SSLAPB_NEG_INF;   // w_i = -inf for a single-entry row (:344)
+    o.bid = (bc - wi) + eps;                                   // :360
+    SSLAPB_PROBE(3, o.j ^ o.powner ^ o.pdeg ^ __double2hiint(o.bid) ^ (int)o.pstart);
+    return o;
+}
 
 template <int W>
 __device__ __forceinline__ void row_bid(const int *__restrict__ cols, const double *__restrict__ vals,
                                         const double *price, long long start, long long end, int t, double eps,
                                         int &jbest, double &bid)
 {
-    const int4 *c4 = reinterpret_cast<const int4 *>(cols);
-    const double2 *v2 = reinterpret_cast<const double2 *>(vals);
-    double b = SSLAPB_NEG_INF, s = SSLAPB_NEG_INF, bc = 0.0;
-    int bi = -1, bj = -1;
-    const long long c1 = (end + 3) >> 2;
-#pragma unroll 2
-    for (long long ch = (start >> 2) + t; ch < c1; ch += W) {
-        const int4 cj = sslapb_ldg_stream_i4(c4 + ch);
-        const double2 va = sslapb_ldg_stream_d2(v2 + 2 * ch);
-        const double2 vb = sslapb_ldg_stream_d2(v2 + 2 * ch + 1);
-        const long long e0 = ch << 2;
-        const bool m0 = (e0 >= start) & (e0 < end);
-        const bool m1 = (e0 + 1 >= start) & (e0 + 1 < end);
-        const bool m2 = (e0 + 2 >= start) & (e0 + 2 < end);
-        const bool m3 = (e0 + 3 >= start) & (e0 + 3 < end);
-        const double p0 = m0 ? price[cj.x] : 0.0;
-        const double p1 = m1 ? price[cj.y] : 0.0;
-        const double p2 = m2 ? price[cj.z] : 0.0;
-        const double p3 = m3 ? price[cj.w] : 0.0;
-        const int i0 = (int)(e0 - start);
-        SSLAPB_VISIT(m0, va.x, p0, cj.x, i0)
-        SSLAPB_VISIT(m1, va.y, p1, cj.y, i0 + 1)
-        SSLAPB_VISIT(m2, vb.x, p2, cj.z, i0 + 2)
-        SSLAPB_VISIT(m3, vb.y, p3, cj.w, i0 + 3)
-    }
-    const int mine = bi;
-#pragma unroll
-    for (int off = W / 2; off > 0; off >>= 1) {
-        const double ob = __shfl_xor_sync(SSLAPB_FULL, b, off);
-        const double os = __shfl_xor_sync(SSLAPB_FULL, s, off);
-        const int oi = __shfl_xor_sync(SSLAPB_FULL, bi, off);
-        const bool ow = (ob > b) || (ob == b && oi > bi);      // larger row index wins equal values (:351)
-        s = ow ? fmax(os, b) : fmax(s, ob);
-        b = ow ? ob : b;
-        bi = ow ? oi : bi;
-    }
-    const unsigned gmask = (W == 32) ? SSLAPB_FULL : (((1u << (W & 31)) - 1u) << ((threadIdx.x & 31) & ~(W - 1)));
-    const unsigned own = __ballot_sync(SSLAPB_FULL, mine >= 0 && mine == bi) & gmask;
-    const int src = own ? (__ffs(own) - 1) : (threadIdx.x & 31);
-    bc = __shfl_sync(SSLAPB_FULL, bc, src);
-    bj = __shfl_sync(SSLAPB_FULL, bj, src);
-    jbest = own ? bj : -1;
-    bid = (bc - s) + eps;                                      // :360
+    const SslapbBid o = row_bid_core<W, false>(cols, vals, price, nullptr, start, end, t, eps);
+    jbest = o.j;
+    bid = o.bid;
+}
+
+template <int W>
+__device__ __forceinline__ SslapbBid row_bid_rec(const int *__restrict__ cols, const double *__restrict__ vals,
+                                                 const SslapbObjRec *rec, long long start, long long end, int t,
+                                                 double eps, long long *acc = nullptr)
+{
+    return row_bid_core<W, true>(cols, vals, nullptr, rec, start, end, t, eps, acc);
 }
 
 // eCE / objective sweep of one row by a full warp (auction_.pyx:460-483 and :504-521).
@@ -94,8 +205,11 @@ __device__ __forceinline__ void row_ece(const int *__restrict__ cols, const doub
     const double2 *v2 = reinterpret_cast<const double2 *>(vals);
     double vm = SSLAPB_NEG_INF, ch_v = 0.0, cs = 0.0;
     int ch_i = -1;
-    const long long c1 = (end + 3) >> 2;
-    for (long long ch = (start >> 2) + lane; ch < c1; ch += 32) {
+    const long long c0 = start >> 2, c1 = (end + 3) >> 2;
+    const int trips = __shfl_sync(SSLAPB_FULL, (int)((c1 - c0 + 31) / 32), 0);
+    for (int it = 0; it < trips; ++it) {
+        const long long ch = c0 + (long long)it * 32 + lane;
+        if (ch >= c1) continue;
         const int4 cj = sslapb_ldg_stream_i4(c4 + ch);
         const double2 va = sslapb_ldg_stream_d2(v2 + 2 * ch);
         const double2 vb = sslapb_ldg_stream_d2(v2 + 2 * ch + 1);
@@ -160,34 +274,47 @@ __device__ __forceinline__ bool grid_barrier(SslapbCtrl *c, unsigned nblk, unsig
 
 // ----------------------------------------------------------------------------------------------------------------------
 // Warp-list regime: merge + assignment + list compaction for nu <= 32 bidders, executed by ONE warp.
-// Lane a < nu holds list position a: person `li`, its object `j` and bid `bid`.  Returns the new count; `li` becomes
-// the new list entry of position `lane` (-1 beyond the new count).  Restates auction_.pyx:375-430.
+// Lane a < nu holds list position a: person `li` with CSR row [lst, lst+ldg), and its bid `B` (object, value, record of
+// the object's current owner).  Returns the new count; (li,lst,ldg) become the new list entry of position `lane`.
+// Restates auction_.pyx:375-430.
 // ----------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int warp_resolve(const SslapbAuctionParams &P, int nu, int &li, int j, double bid)
+__device__ __forceinline__ int warp_resolve(const SslapbAuctionParams &P, int nu, int &li, long long &lst, int &ldg,
+                                            const SslapbBid &B)
 {
     const int lane = threadIdx.x & 31;
     const bool act = lane < nu;
+    const int j = B.j;
+    const double bid = B.bid;
     bool win = act && j >= 0;
-    if (nu > 1) {
+    // bidders on the same object: only then is there anything to merge (rare for small frontiers)
+    const unsigned peers = __match_any_sync(SSLAPB_FULL, win ? j : (-1 - lane));
+    if (__any_sync(SSLAPB_FULL, peers != (1u << lane))) {
         for (int s = 0; s < nu; ++s) {
             const int oj = __shfl_sync(SSLAPB_FULL, j, s);
             const double ob = __shfl_sync(SSLAPB_FULL, bid, s);
+            // strict '>' at :379: the earliest bidder in list order keeps an equal bid
             if (act && s != lane && oj == j && (ob > bid || (ob == bid && s < lane))) win = false;
         }
     }
     int nv = act ? li : -1;
+    long long nst = lst;
+    int ndg = ldg;
     if (win) {
-        const int prev = P.owner[j];
-        P.price[j] = bid;                                      // :397
-        P.owner[j] = li;                                       // :418
+        SslapbObjRec r;
+        r.start = lst; r.owner = li; r.deg = ldg; r.price = bid; r.pad = 0;
+        *reinterpret_cast<int4 *>(P.rec + j) = *reinterpret_cast<const int4 *>(&r);      // owner + its row (:418)
+        P.rec[j].price = bid;                                  // :397
+        P.price[j] = bid;
         P.p2o[li] = j;                                         // :417
-        if (prev >= 0) P.p2o[prev] = -1;                       // :404
-        nv = prev;                                             // evicted owner takes the slot (:409) or hole (:412)
+        if (B.powner >= 0) P.p2o[B.powner] = -1;               // :404
+        nv = B.powner;                                         // evicted owner takes the slot (:409) or hole (:412)
+        nst = B.pstart; ndg = B.pdeg;
     }
     __syncwarp();
     const unsigned valid = nu >= 32 ? SSLAPB_FULL : ((1u << nu) - 1u);
     const unsigned holes = __ballot_sync(SSLAPB_FULL, act && nv < 0);
     const int new_nu = nu - __popc(holes);                     // :429
+    if (holes == 0u) { li = nv; lst = nst; ldg = ndg; return new_nu; }
     const unsigned leftm = new_nu >= 32 ? SSLAPB_FULL : ((1u << new_nu) - 1u);
     const unsigned left_holes = holes & leftm;
     const unsigned right_live = valid & ~holes & ~leftm;
@@ -199,85 +326,184 @@ __device__ __forceinline__ int warp_resolve(const SslapbAuctionParams &P, int nu
         src = __ffs(m) - 1;
     }
     const int v = __shfl_sync(SSLAPB_FULL, nv, src & 31);
+    const long long vs = __shfl_sync(SSLAPB_FULL, nst, src & 31);
+    const int vd = __shfl_sync(SSLAPB_FULL, ndg, src & 31);
     li = lane < new_nu ? v : -1;
+    lst = vs; ldg = vd;
     return new_nu;
 }
 
-// CTA 0 finishes the eps-phase alone once nu <= t_small (nu only shrinks inside a phase).
-__device__ __noinline__ void small_regime(const SslapbAuctionParams &P, SslapbCtrl *C, int nu, float eps_f,
-                                          long long its, long long max_iter)
+// Loads of one 4-entry chunk of a row (hop 1 of a round).
+struct SslapbChunk { int4 cj; double2 va, vb; };
+__device__ __forceinline__ SslapbChunk sslapb_load_chunk(const int *__restrict__ cols, const double *__restrict__ vals,
+                                                         long long ch, bool active)
 {
-    __shared__ int s_list[32];
-    __shared__ int s_j[32];
-    __shared__ double s_bid[32];
+    SslapbChunk c;
+    c.cj = make_int4(0, 0, 0, 0); c.va = make_double2(0.0, 0.0); c.vb = c.va;
+    if (active) {
+        c.cj = __ldg(reinterpret_cast<const int4 *>(cols) + ch);
+        c.va = __ldg(reinterpret_cast<const double2 *>(vals) + 2 * ch);
+        c.vb = __ldg(reinterpret_cast<const double2 *>(vals) + 2 * ch + 1);
+    }
+    return c;
+}
+
+// Single-bidder chain (52 % of all rounds at N = 100k): person i bids, wins (there is no competitor), evicts the owner i'
+// of the object, i' bids, ...  One warp, no barrier.  Software-pipelined: as soon as the winning entry is known (3 REDUX
+// after the record gather) the evicted owner's row is requested; the second-best reduction, the bid arithmetic and the
+// stores of the current round overlap that load.  Dependent chain per round = row entries -> object records -> top-1.
+// Rows longer than one warp pass (> 125 entries) take the generic path.  Returns the new count (0 or 1).
+__device__ __forceinline__ int chain_rounds(const SslapbAuctionParams &P, double eps, int &li, long long &lst, int &ldg,
+                                            long long &its, long long max_iter, int &done, long long &rounds)
+{
+    const int lane = threadIdx.x & 31;
+    li = __shfl_sync(SSLAPB_FULL, li, 0); lst = __shfl_sync(SSLAPB_FULL, lst, 0); ldg = __shfl_sync(SSLAPB_FULL, ldg, 0);
+    int nu = 1;
+    long long c0 = lst >> 2, c1 = (lst + ldg + 3) >> 2;
+    bool single = (c1 - c0) <= 32;
+    SslapbChunk cur = sslapb_load_chunk(P.cols, P.vals, c0 + lane, single && (c0 + lane < c1));
+    while (nu == 1 && !done) {
+        SslapbBid B;
+        if (!single) {                                         // long row: generic sweep, nothing prefetched
+            B = row_bid_rec<32>(P.cols, P.vals, P.rec, lst, lst + ldg, lane, eps);
+            nu = warp_resolve(P, 1, li, lst, ldg, B);
+            li = __shfl_sync(SSLAPB_FULL, li, 0); lst = __shfl_sync(SSLAPB_FULL, lst, 0); ldg = __shfl_sync(SSLAPB_FULL, ldg, 0);
+            ++its; ++rounds;
+            if (its >= max_iter) done = 3;
+            if (nu == 1) {
+                c0 = lst >> 2; c1 = (lst + ldg + 3) >> 2; single = (c1 - c0) <= 32;
+                cur = sslapb_load_chunk(P.cols, P.vals, c0 + lane, single && (c0 + lane < c1));
+            }
+            continue;
+        }
+        const long long ch = c0 + lane;
+        const bool active = ch < c1;
+        const int lo = (int)(lst - (ch << 2)), hi = active ? (int)min(lst + ldg - (ch << 2), 4ll) : 0;
+        const bool m0 = (0 >= lo) & (0 < hi), m1 = (1 >= lo) & (1 < hi), m2 = (2 >= lo) & (2 < hi), m3 = (3 >= lo) & (3 < hi);
+        const int4 cj = cur.cj;
+        const int4 z = make_int4(0, 0, -1, 0);
+        const int4 r0 = m0 ? *reinterpret_cast<const int4 *>(P.rec + cj.x) : z;
+        const int4 r1 = m1 ? *reinterpret_cast<const int4 *>(P.rec + cj.y) : z;
+        const int4 r2 = m2 ? *reinterpret_cast<const int4 *>(P.rec + cj.z) : z;
+        const int4 r3 = m3 ? *reinterpret_cast<const int4 *>(P.rec + cj.w) : z;
+        const double p0 = m0 ? P.rec[cj.x].price : 0.0;
+        const double p1 = m1 ? P.rec[cj.y].price : 0.0;
+        const double p2 = m2 ? P.rec[cj.z].price : 0.0;
+        const double p3 = m3 ? P.rec[cj.w].price : 0.0;
+        const unsigned long long k0 = sslapb_vkey(cur.va.x, p0, m0), k1 = sslapb_vkey(cur.va.y, p1, m1);
+        const unsigned long long k2 = sslapb_vkey(cur.vb.x, p2, m2), k3 = sslapb_vkey(cur.vb.y, p3, m3);
+        const bool w01 = k1 >= k0, w23 = k3 >= k2;
+        const unsigned long long b01 = w01 ? k1 : k0, l01 = w01 ? k0 : k1;
+        const unsigned long long b23 = w23 ? k3 : k2, l23 = w23 ? k2 : k3;
+        const bool wf = b23 >= b01;
+        const unsigned long long b = wf ? b23 : b01;
+        const unsigned long long s = wf ? (b01 > l23 ? b01 : l23) : (b23 > l01 ? b23 : l01);
+        const int w4 = wf ? (w23 ? 3 : 2) : (w01 ? 1 : 0);
+        const int bi = b ? (int)((ch << 2) - lst) + w4 : -1;
+        const int4 br = (w4 & 2) ? ((w4 & 1) ? r3 : r2) : ((w4 & 1) ? r1 : r0);
+        // top-1 across the warp -> who is evicted -> request its row right away
+        const unsigned bh = (unsigned)(b >> 32), bl = (unsigned)b;
+        const unsigned khi = __reduce_max_sync(SSLAPB_FULL, bh);
+        const unsigned klo = __reduce_max_sync(SSLAPB_FULL, bh == khi ? bl : 0u);
+        const bool top = (bh == khi) & (bl == klo);
+        const int widx = __reduce_max_sync(SSLAPB_FULL, top ? bi : -1);
+        const bool iswin = top & (bi == widx) & (bi >= 0);
+        const unsigned own = __ballot_sync(SSLAPB_FULL, iswin);
+        if (own == 0u) { done = 4; break; }                    // empty row: cannot happen (rejected at CSR build)
+        const int src = __ffs(own) - 1;
+        const int powner = __shfl_sync(SSLAPB_FULL, br.z, src);
+        const int pdeg = __shfl_sync(SSLAPB_FULL, br.w, src);
+        const int sx = __shfl_sync(SSLAPB_FULL, br.x, src), sy = __shfl_sync(SSLAPB_FULL, br.y, src);
+        const long long pstart = (long long)(((unsigned long long)(unsigned)sy << 32) | (unsigned)sx);
+        const bool more = (powner >= 0) && (its + 1 < max_iter);
+        const long long n0 = pstart >> 2, n1 = (pstart + pdeg + 3) >> 2;
+        const bool nsingle = (n1 - n0) <= 32;
+        const SslapbChunk nxt = sslapb_load_chunk(P.cols, P.vals, n0 + lane, more && nsingle && (n0 + lane < n1));
+        // ---- the rest of this round overlaps the load above
+        const unsigned long long cand = iswin ? s : b;
+        const unsigned chh = (unsigned)(cand >> 32), chl = (unsigned)cand;
+        const unsigned shi = __reduce_max_sync(SSLAPB_FULL, chh);
+        const unsigned slo = __reduce_max_sync(SSLAPB_FULL, chh == shi ? chl : 0u);
+        const unsigned long long skey = ((unsigned long long)shi << 32) | slo;
+        const double myc = (w4 & 2) ? ((w4 & 1) ? cur.vb.y : cur.vb.x) : ((w4 & 1) ? cur.va.y : cur.va.x);
+        const int myj = (w4 & 2) ? ((w4 & 1) ? cj.w : cj.z) : ((w4 & 1) ? cj.y : cj.x);
+        const double bc = __shfl_sync(SSLAPB_FULL, myc, src);
+        const int j = __shfl_sync(SSLAPB_FULL, myj, src);
+        const double wi = skey ? sslapb_key2double(skey) : SSLAPB_NEG_INF;
+        const double bid = (bc - wi) + eps;                    // :360
+        if (lane == 0) {                                       // the only bidder wins (:379-385, :394-427)
+            SslapbObjRec r;
+            r.start = lst; r.owner = li; r.deg = ldg; r.price = bid; r.pad = 0;
+            *reinterpret_cast<int4 *>(P.rec + j) = *reinterpret_cast<const int4 *>(&r);
+            P.rec[j].price = bid;
+            P.price[j] = bid;
+            P.p2o[li] = j;
+            if (powner >= 0) P.p2o[powner] = -1;
+        }
+        __syncwarp();
+        ++its; ++rounds;
+        if (its >= max_iter) done = 3;
+        if (powner < 0) { nu = 0; li = -1; break; }            // nobody evicted: the frontier is empty
+        li = powner; lst = pstart; ldg = pdeg;                 // the evicted owner is the next (and only) bidder
+        c0 = n0; c1 = n1; single = nsingle; cur = nxt;
+    }
+    return nu;
+}
+
+// CTA 0 finishes the eps-phase alone once nu <= t_small (nu only shrinks inside a phase).
+__device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, SslapbCtrl *C, int nu, float eps_f,
+                                             long long its, long long max_iter)
+{
+    __shared__ int s_list[32], s_deg[32];
+    __shared__ long long s_start[32];
+    __shared__ SslapbBid s_bid[32];
     __shared__ int s_nu, s_done;
     __shared__ long long s_its, s_rw, s_rs;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // warp index through a shuffle: tells the compiler it is warp-uniform (same idiom as cutlass::canonical_warp_idx_sync)
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(SSLAPB_FULL, tid >> 5, 0);
     const double eps = (double)eps_f;
-    int li = -1, done = 0;
+    int li = -1, ldg = 0, done = 0;
+    long long lst = 0;
     long long rw = 0, rs = 0;
     if (warp == 0) {
         if (lane < nu) {
             const int v = P.list[lane];
             li = v < -1 ? P.mover[-(v + 2)] : v;               // grid regime leaves rank-encoded holes, see below
-            s_list[lane] = li;
+            lst = __ldg(P.rowptr + li);
+            ldg = (int)(__ldg(P.rowptr + li + 1) - lst);
+            s_list[lane] = li; s_start[lane] = lst; s_deg[lane] = ldg;
         }
     }
     __syncthreads();
 
-    // ---- warp regime: one warp per bidder, 2 block barriers per round
-    while (nu > SOLO_MAX && !done) {
-        if (warp < nu) {
-            const int i = s_list[warp];
-            const long long st = __ldg(P.rowptr + i), en = __ldg(P.rowptr + i + 1);
-            int j; double bid;
-            row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);
-            if (lane == 0) { s_j[warp] = j; s_bid[warp] = bid; }
+    unsigned long long tw0 = sslapb_globaltimer();
+    // ---- warp regime (2..32 bidders): one warp per bidder, 2 block barriers per round
+    while (nu > 1 && !done) {
+        for (int a = warp; a < nu; a += SSLAPB_THREADS / 32) {
+            const long long st = s_start[a];
+            const SslapbBid b = row_bid_rec<32>(P.cols, P.vals, P.rec, st, st + s_deg[a], lane, eps);
+            if (lane == 0) s_bid[a] = b;
         }
         __syncthreads();
         if (warp == 0) {
-            const int j = lane < nu ? s_j[lane] : -1;
-            const double bid = lane < nu ? s_bid[lane] : 0.0;
-            nu = warp_resolve(P, nu, li, j, bid);
+            SslapbBid b;
+            if (lane < nu) b = s_bid[lane]; else { b.j = -1; b.bid = 0.0; b.powner = -1; b.pdeg = 0; b.pstart = 0; }
+            nu = warp_resolve(P, nu, li, lst, ldg, b);
             ++its; ++rw;
             if (its >= max_iter) done = 3;
-            if (lane < 32) s_list[lane] = li;
+            s_list[lane] = li; s_start[lane] = lst; s_deg[lane] = ldg;
             if (lane == 0) { s_nu = nu; s_done = done; s_its = its; }
         }
         __syncthreads();
-        nu = s_nu; done = s_done; its = s_its;
+        nu = __shfl_sync(SSLAPB_FULL, s_nu, 0); done = __shfl_sync(SSLAPB_FULL, s_done, 0);
+        its = __shfl_sync(SSLAPB_FULL, s_its, 0);
     }
 
-    // ---- solo regime: warp 0 alone, 32 / 16 / 8 lanes per bidder, no block barrier
+    unsigned long long tw1 = sslapb_globaltimer();
+    // ---- single-bidder chain: warp 0 alone, no block barrier
     if (warp == 0) {
-        while (nu > 0 && !done) {
-            int j, pj; double bid, pb;
-            if (nu == 1) {
-                const int i = __shfl_sync(SSLAPB_FULL, li, 0);
-                const long long st = __ldg(P.rowptr + i), en = __ldg(P.rowptr + i + 1);
-                row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);
-                pj = j; pb = bid;
-            } else if (nu == 2) {
-                const int g = lane >> 4;
-                const int i = __shfl_sync(SSLAPB_FULL, li, g);
-                const long long st = __ldg(P.rowptr + i), en = __ldg(P.rowptr + i + 1);
-                row_bid<16>(P.cols, P.vals, P.price, st, en, lane & 15, eps, j, bid);
-                pj = __shfl_sync(SSLAPB_FULL, j, (lane << 4) & 31);
-                pb = __shfl_sync(SSLAPB_FULL, bid, (lane << 4) & 31);
-            } else {
-                const int g = lane >> 3;
-                const int i = __shfl_sync(SSLAPB_FULL, li, g);
-                long long st = 0, en = 0;
-                if (g < nu) { st = __ldg(P.rowptr + i); en = __ldg(P.rowptr + i + 1); }
-                row_bid<8>(P.cols, P.vals, P.price, st, en, lane & 7, eps, j, bid);
-                pj = __shfl_sync(SSLAPB_FULL, j, (lane << 3) & 31);
-                pb = __shfl_sync(SSLAPB_FULL, bid, (lane << 3) & 31);
-            }
-            nu = warp_resolve(P, nu, li, pj, pb);
-            ++its; ++rs;
-            if (its >= max_iter) done = 3;
-        }
+        if (nu == 1 && !done) nu = chain_rounds(P, eps, li, lst, ldg, its, max_iter, done, rs);
         if (lane == 0) { s_nu = nu; s_done = done; s_its = its; s_rw = rw; s_rs = rs; }
         if (nu > 0 && lane < nu) P.list[lane] = li;            // only reachable through max_iter
     }
@@ -285,9 +511,12 @@ __device__ __noinline__ void small_regime(const SslapbAuctionParams &P, SslapbCt
     if (tid == 0) {
         C->nu = s_nu;
         C->its = s_its;
-        if (s_done) C->done = s_done;
+        if (s_done == 4) *(volatile int *)&C->abort_flag = 2;
+        else if (s_done) C->done = s_done;
         C->rounds_warp += s_rw;
         C->rounds_solo += s_rs;
+        C->prof[3] += tw1 - tw0;
+        C->prof[4] += sslapb_globaltimer() - tw1;
     }
 }
 
@@ -321,10 +550,10 @@ __device__ __forceinline__ int block_excl_scan_flag(bool flag, int &total)
 
 #define GB() do { if (!grid_barrier(C, nblk, P.watchdog_ns)) return; } while (0)
 
-__global__ void __launch_bounds__(1024, 1) sslapb_auction_kernel(SslapbAuctionParams P)
+__global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(SslapbAuctionParams P)
 {
     SslapbCtrl *C = P.ctrl;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(SSLAPB_FULL, tid >> 5, 0);
     const unsigned nblk = gridDim.x;
     const int wpc = blockDim.x >> 5;
     const int gwarp = blockIdx.x * wpc + warp;
@@ -338,8 +567,8 @@ __global__ void __launch_bounds__(1024, 1) sslapb_auction_kernel(SslapbAuctionPa
 
     for (;;) {
         // ---- loop top: every CTA arrives here right after a grid barrier; the control block is stable
-        int nu = *(volatile int *)&C->nu;
-        int done = *(volatile int *)&C->done;
+        int nu = __shfl_sync(SSLAPB_FULL, *(volatile int *)&C->nu, 0);        // shuffles: warp-uniform for the compiler
+        int done = __shfl_sync(SSLAPB_FULL, *(volatile int *)&C->done, 0);
         const float eps_f = *(volatile float *)&C->eps;
         const long long its = *(volatile long long *)&C->its;
         const long long max_iter = *(volatile long long *)&C->max_iter;
@@ -348,6 +577,8 @@ __global__ void __launch_bounds__(1024, 1) sslapb_auction_kernel(SslapbAuctionPa
         if (nu > P.t_small) {
             // ================================ grid regime: one round ================================
             const double eps = (double)eps_f;
+            unsigned long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0, tp5 = 0;
+            if (gtid == 0) tp0 = sslapb_globaltimer();
             // (1) bidding: warp per list position (auction_.pyx:339-365) + per-object atomicMax merge (:375-385)
             for (int a = gwarp; a < nu; a += nwarps) {
                 int v = P.list[a];
@@ -370,8 +601,10 @@ __global__ void __launch_bounds__(1024, 1) sslapb_auction_kernel(SslapbAuctionPa
                     }
                 }
             }
+            if (gtid == 0) tp1 = sslapb_globaltimer();
             GB();
-            const int tie = *(volatile int *)&C->tie_flag;
+            if (gtid == 0) tp2 = sslapb_globaltimer();
+            const int tie = __shfl_sync(SSLAPB_FULL, *(volatile int *)&C->tie_flag, 0);
             const int L = (nu + (int)nblk - 1) / (int)nblk;    // each CTA owns a contiguous chunk of positions
             const int lo = min(nu, (int)blockIdx.x * L), hi = min(nu, lo + L);
             if (tie) {                                         // (1b) equal best bids: earliest list position wins (:379)
@@ -389,9 +622,13 @@ __global__ void __launch_bounds__(1024, 1) sslapb_auction_kernel(SslapbAuctionPa
                 const bool win = (P.bidkey[j] == sslapb_ord64(bid)) && (!tie || P.winpos[j] == a);
                 if (win) {
                     const int i = P.list[a];
-                    const int prev = P.owner[j];
+                    const int prev = P.rec[j].owner;
+                    SslapbObjRec r;
+                    r.start = __ldg(P.rowptr + i); r.owner = i; r.deg = (int)(__ldg(P.rowptr + i + 1) - r.start);
+                    r.price = bid; r.pad = 0;
+                    *reinterpret_cast<int4 *>(P.rec + j) = *reinterpret_cast<const int4 *>(&r);
+                    P.rec[j].price = bid;
                     P.price[j] = bid;
-                    P.owner[j] = i;
                     P.p2o[i] = j;
                     if (prev >= 0) P.p2o[prev] = -1; else ++myholes;
                     P.list[a] = prev;                          // evicted owner takes the slot, or -1 = hole
@@ -404,7 +641,9 @@ __global__ void __launch_bounds__(1024, 1) sslapb_auction_kernel(SslapbAuctionPa
             if (myholes) atomicAdd(&s_red, myholes);
             __syncthreads();
             if (tid == 0) P.hole_count[blockIdx.x] = s_red;
+            if (gtid == 0) tp3 = sslapb_globaltimer();
             GB();
+            if (gtid == 0) tp4 = sslapb_globaltimer();
             // (3) push_all_left (:137-162): k-th hole left of new_nu <- k-th live entry right of it
             if (warp == 0) {                                   // per-CTA hole counts -> total, my prefix, prefix of the split chunk
                 int ht = 0, hp = 0;
@@ -426,7 +665,7 @@ __global__ void __launch_bounds__(1024, 1) sslapb_auction_kernel(SslapbAuctionPa
                 if (lane == 0) { s_hpre[0] = h2; s_hpre[1] = hp; s_hpre[2] = ht; s_red = 0; }
             }
             __syncthreads();
-            const int H = s_hpre[2], hpre = s_hpre[1];
+            const int H = __shfl_sync(SSLAPB_FULL, s_hpre[2], 0), hpre = __shfl_sync(SSLAPB_FULL, s_hpre[1], 0);
             const int new_nu = nu - H;
             const int cb = new_nu / L;                         // chunk that contains the split point
             int cnt = 0;
@@ -458,20 +697,27 @@ __global__ void __launch_bounds__(1024, 1) sslapb_auction_kernel(SslapbAuctionPa
                 C->tie_flag = 0;
                 C->rounds_grid += 1;
                 if (its + 1 >= max_iter) C->done = 3;
+                tp5 = sslapb_globaltimer();
             }
             GB();
+            if (gtid == 0) {
+                C->prof[0] += tp1 - tp0; C->prof[1] += tp3 - tp2; C->prof[2] += tp5 - tp4;
+                C->prof[7] += (tp2 - tp1) + (tp4 - tp3) + (sslapb_globaltimer() - tp5);
+            }
         } else {
             // ================================ warp-list regimes: CTA 0 finishes the phase ================================
             if (blockIdx.x == 0) small_regime(P, C, nu, eps_f, its, max_iter);
             GB();
         }
 
-        nu = *(volatile int *)&C->nu;
-        done = *(volatile int *)&C->done;
+        nu = __shfl_sync(SSLAPB_FULL, *(volatile int *)&C->nu, 0);
+        done = __shfl_sync(SSLAPB_FULL, *(volatile int *)&C->done, 0);
         if (done || nu != 0) continue;
 
         // ================================ full assignment reached: terminate() / eps-scaling (:275-292) ================================
         {
+            unsigned long long te0 = 0;
+            if (gtid == 0) te0 = sslapb_globaltimer();
             const float teps = *(volatile float *)&C->target_eps;
             const double eps_t = (double)teps;
             bool viol = false;
@@ -491,7 +737,7 @@ __global__ void __launch_bounds__(1024, 1) sslapb_auction_kernel(SslapbAuctionPa
             const bool stop_eps = !stop_opt && (eps_now < teps);   // :280
             if (!stop_opt && !stop_eps) {                      // :283-292 next phase: prices kept, everything else reset
                 for (int i = gtid; i < P.N; i += nthreads) { P.p2o[i] = -1; P.list[i] = i; }
-                for (int j = gtid; j < P.M; j += nthreads) P.owner[j] = -1;
+                for (int j = gtid; j < P.M; j += nthreads) P.rec[j].owner = -1;
             }
             GB();
             if (gtid == 0) {
@@ -503,6 +749,7 @@ __global__ void __launch_bounds__(1024, 1) sslapb_auction_kernel(SslapbAuctionPa
                     C->nu = P.N;
                 }
                 C->ece_viol = 0;
+                C->prof[5] += sslapb_globaltimer() - te0;
             }
             GB();
         }
@@ -564,20 +811,23 @@ __global__ void sslapb_auction_init_kernel(SslapbAuctionParams P)
 {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, n = gridDim.x * blockDim.x;
     for (int i = gtid; i < P.N; i += n) { P.p2o[i] = -1; P.list[i] = i; }
-    for (int j = gtid; j < P.M; j += n) { P.owner[j] = -1; P.price[j] = 0.0; P.bidkey[j] = 0ull; P.winpos[j] = 0x7fffffff; }
+    for (int j = gtid; j < P.M; j += n) {
+        SslapbObjRec r; r.start = 0; r.owner = -1; r.deg = 0; r.price = 0.0; r.pad = 0;
+        P.rec[j] = r; P.price[j] = 0.0; P.bidkey[j] = 0ull; P.winpos[j] = 0x7fffffff;
+    }
 }
 
 extern "C" cudaError_t sslapb_launch_auction(const SslapbAuctionParams *P, int grid, cudaStream_t stream)
 {
     sslapb_auction_init_kernel<<<grid, 1024, 0, stream>>>(*P);
     void *args[] = {(void *)P};
-    return cudaLaunchCooperativeKernel((const void *)sslapb_auction_kernel, dim3(grid), dim3(1024), args, 0, stream);
+    return cudaLaunchCooperativeKernel((const void *)sslapb_auction_kernel, dim3(grid), dim3(SSLAPB_THREADS), args, 0, stream);
 }
 
 extern "C" cudaError_t sslapb_auction_grid_size(int device, int *grid)
 {
     int per_sm = 0, sms = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sslapb_auction_kernel, 1024, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sslapb_auction_kernel, SSLAPB_THREADS, 0);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;

@@ -20,6 +20,21 @@ struct SslapbCtrl {
     int ece_final;            // meta['eCE'] (:297); -1 until known
     long long rounds_grid, rounds_warp, rounds_solo;   // instrumentation: rounds executed per regime
     unsigned long long t_begin, t_end;                 // %globaltimer at kernel start / end
+    unsigned long long prof2[8];                       // diagnostic builds (-DSSLAPB_PROFILE_SOLO): SM cycles inside single-bidder rounds
+    unsigned long long prof[8];                        // ns spent (CTA 0 view): 0 grid bid, 1 grid tie+assign, 2 grid compaction,
+                                                       // 3 warp regime, 4 solo regime, 5 eCE/phase change, 6 epilogue, 7 barriers of the grid regime
+};
+
+// Per-object record (32 B = one sector): everything a bidder needs to know about the object it wins, so that the
+// warp-list regimes need only two dependent memory hops per round (row entries -> records) instead of four
+// (owner -> its row offsets -> row entries -> prices).  `price` mirrors price[] (which the grid regime gathers from,
+// 8 B per object, L1 friendly); start/deg describe the CSR row of the current owner.
+struct __align__(32) SslapbObjRec {
+    long long start;          // first CSR entry of the owner's row
+    int owner;                // object_to_person (auction_.pyx:232); -1 = unowned
+    int deg;                  // number of entries of the owner's row
+    double price;             // copy of price[j]
+    long long pad;
 };
 
 struct SslapbAuctionParams {
@@ -28,7 +43,7 @@ struct SslapbAuctionParams {
     const int *cols;          // flat_j (:229); 16-byte aligned base, >= 4 entries of slack after nnz
     const double *vals;       // sign-folded values ('min' negated, :236-237); same alignment/slack
     double *price;            // p (:220)
-    int *owner;               // object_to_person (:232)
+    SslapbObjRec *rec;        // per-object record incl. object_to_person (:232)
     int *p2o;                 // person_to_object (:231)
     int *list;                // unassigned_people (:260), positions [0,nu)
     int *mover;               // grid-mode compaction: k-th live entry right of the new count

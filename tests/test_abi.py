@@ -39,7 +39,7 @@ def test_meta_struct_layout_matches_header():
     for decl in body.split(";"):
         decl = decl.strip()
         if decl:
-            names += [n.strip() for n in decl.split(None, 1)[1].split(",")]
+            names += [re.sub(r"\[\d+\]", "", n.strip()) for n in decl.split(None, 1)[1].split(",")]
     assert names == [f[0] for f in nat.Meta._fields_]
     assert ctypes.sizeof(nat.Meta) % 8 == 0
 

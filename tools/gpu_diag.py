@@ -41,7 +41,7 @@ def compare(name, loc, val, problem="min", t_small=32, max_iter=1000000, **kw):
     print(f"[{name}] t_small={t_small} {'OK ' if ok else 'MISMATCH'} sol={same_sol} prices={same_p} diffs={diffs} "
           f"its={g['meta']['its']} rounds(g/w/s)={r.rounds_grid}/{r.rounds_warp}/{r.rounds_solo} "
           f"solve={r.solve_ms:.3f}ms setup={r.setup_ms:.3f}ms h2d={r.h2d_ms:.3f}ms wall={tg*1e3:.1f}ms "
-          f"oracle={o['meta']['_raw']['seconds']*1e3:.1f}ms", flush=True)
+          f"oracle={o['meta']['_raw']['seconds']*1e3:.1f}ms prof={[round(x,2) for x in r.prof_ms]}", flush=True)
     return ok
 
 

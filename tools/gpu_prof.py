@@ -1,0 +1,35 @@
+"""Per-regime device-time profile of the persistent kernel on C2 / C3 (python tools/gpu_prof.py [c2|c3|both])."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import sslap_b200
+from sslap_b200 import _native as nat
+from sslap_b200.datagen import make_problem
+import ctypes as C
+h = nat.default_handle(); L = nat.load()
+which = sys.argv[1] if len(sys.argv) > 1 else "both"
+names = ["grid_bid", "grid_assign", "grid_compact", "warp", "solo", "ece_phase", "-", "grid_barriers"]
+def run(tag, n, d, reps=2, **kw):
+    loc, val = make_problem(n, d, "float", seed=0)
+    for r in range(reps):
+        t = time.perf_counter()
+        g = sslap_b200.auction_solve(loc=loc, val=val, size=(n, n), cardinality_check=False, _raw_meta=True, **kw)
+        w = time.perf_counter() - t
+        m = g["raw"]
+        print(f"[{tag}] its={m.its} rounds g/w/s={m.rounds_grid}/{m.rounds_warp}/{m.rounds_solo} solve={m.solve_ms:.2f}ms "
+              f"setup={m.setup_ms:.2f} h2d={m.h2d_ms:.2f} wall={w*1e3:.1f}ms", flush=True)
+        print("    " + "  ".join(f"{k}={v:.2f}ms" for k, v in zip(names, m.prof_ms)))
+        per = lambda t, c: (1e3 * t / c) if c else 0.0
+        print(f"    per-round us: grid={per(m.prof_ms[0]+m.prof_ms[1]+m.prof_ms[2]+m.prof_ms[7], m.rounds_grid):.2f} "
+              f"(barriers {per(m.prof_ms[7], m.rounds_grid):.2f}) warp={per(m.prof_ms[3], m.rounds_warp):.2f} solo={per(m.prof_ms[4], m.rounds_solo):.2f}", flush=True)
+    return loc, val
+if which in ("c2", "both"):
+    run("C2", 10000, 0.01)
+if which in ("c3", "both"):
+    loc, val = run("C3", 100000, 0.001)
+    n = 100000
+    for flush in (0, 1):
+        ms = C.c_float(0)
+        rc = L.sslapb_bid_sweep(h.ptr, None, None, n, 0.5, 1, 20, flush, None, None, C.byref(ms))
+        by = 12 * val.size + 36 * n
+        print(f"[C3 full sweep flush={flush}] rc={rc} {ms.value*1e3:.1f} us  {by/ms.value/1e6:.1f} GB/s  frac={by/ms.value/1e6/6544:.3f}", flush=True)
