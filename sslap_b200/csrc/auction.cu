@@ -238,34 +238,29 @@ __device__ __forceinline__ void row_ece(const int *__restrict__ cols, const doub
 }
 
 // ----------------------------------------------------------------------------------------------------------------------
-// Grid barrier (sense by generation).  Returns false when the solve was aborted (watchdog / internal assert).
+// Grid barrier: ONE release-add per CTA on a monotonically increasing counter, then acquire-polling of the same word
+// until it reaches `target` (= barriers passed so far * #CTAs; every CTA counts its barriers in a register, so there is
+// no reset and no generation word).  Returns false when the solve was aborted (watchdog / internal assert).
 // ----------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool grid_barrier(SslapbCtrl *c, unsigned nblk, unsigned long long watchdog_ns)
+__device__ __forceinline__ bool grid_barrier(SslapbCtrl *c, unsigned nblk, unsigned &epoch, unsigned long long watchdog_ns)
 {
     __shared__ int s_abort;
+    epoch += nblk;
     __syncthreads();
     if (threadIdx.x == 0) {
         int ab = 0;
-        const unsigned gen = *(volatile unsigned *)&c->bar_gen;
-        __threadfence();
-        const unsigned prev = atomicAdd(&c->bar_count, 1u);
-        if (prev == nblk - 1) {
-            *(volatile unsigned *)&c->bar_count = 0u;
-            __threadfence();
-            atomicAdd(&c->bar_gen, 1u);
-        } else {
-            unsigned polls = 0, ns = 64;
-            unsigned long long t0 = 0;
-            while (sslapb_ld_acquire_u32(&c->bar_gen) == gen) {
-                if (++polls < 256) continue;                 // short waits (grid rounds): pure spin
-                if (polls == 256) t0 = sslapb_globaltimer();
-                if (sslapb_ld_volatile_s32(&c->abort_flag)) { ab = 1; break; }
-                __nanosleep(ns);                             // long waits (CTA 0 runs the tail alone): back off
-                if (ns < 2048) ns <<= 1;
-                if (sslapb_globaltimer() - t0 > watchdog_ns) { *(volatile int *)&c->abort_flag = 1; ab = 1; break; }
-            }
+        const unsigned target = epoch;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(&c->bar_count) : "memory");
+        unsigned polls = 0, ns = 64;
+        unsigned long long t0 = 0;
+        while ((int)(sslapb_ld_acquire_u32(&c->bar_count) - target) < 0) {
+            if (++polls < 256) continue;                     // short waits (grid rounds): pure spin
+            if (polls == 256) t0 = sslapb_globaltimer();
+            if (sslapb_ld_volatile_s32(&c->abort_flag)) { ab = 1; break; }
+            __nanosleep(ns);                                 // long waits (CTA 0 runs the tail alone): back off
+            if (ns < 2048) ns <<= 1;
+            if (sslapb_globaltimer() - t0 > watchdog_ns) { *(volatile int *)&c->abort_flag = 1; ab = 1; break; }
         }
-        __threadfence();
         s_abort = ab | sslapb_ld_volatile_s32(&c->abort_flag);
     }
     __syncthreads();
@@ -548,7 +543,7 @@ __device__ __forceinline__ int block_excl_scan_flag(bool flag, int &total)
     return s_wtot[warp] + inwarp;
 }
 
-#define GB() do { if (!grid_barrier(C, nblk, P.watchdog_ns)) return; } while (0)
+#define GB() do { if (!grid_barrier(C, nblk, bar_epoch, P.watchdog_ns)) return; } while (0)
 
 __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(SslapbAuctionParams P)
 {
@@ -562,6 +557,7 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
     const int nthreads = nblk * blockDim.x;
     __shared__ int s_red;
     __shared__ int s_hpre[3];
+    unsigned bar_epoch = 0;                                    // barriers passed so far * #CTAs (wraps harmlessly)
 
     if (gtid == 0) C->t_begin = sslapb_globaltimer();
 
