@@ -64,6 +64,7 @@ typedef struct sslapb_meta {
     int64_t rounds_grid, rounds_warp, rounds_solo;   /* rounds executed per regime */
     float   prof_ms[8];      /* device time by section: grid bid, grid assign, grid compaction, warp regime, solo regime,
                                 eCE + phase change, (unused), grid barriers */
+    int64_t prune_second_pass; /* grid-regime rows whose bound-pruned sweep needed the second (exactness) gather pass */
     int32_t stop_reason;     /* 1 target-eps CS holds (:275) | 2 eps < target (:280) | 3 max_iter (:309) */
     int32_t pad;
 } sslapb_meta;
@@ -115,7 +116,8 @@ int sslapb_get_prices(sslapb_handle *h, double *prices_out);
  * Kernel-level entry used by the parity tests and the roofline measurement: one bidding sweep
  * (bid_and_assign's bidding loop, auction_.pyx:339-365) over the CSR of the most recent problem on this handle.
  *   prices (n_cols, host, NULL = keep the handle's current prices), bidders (nb int32, host, NULL = persons 0..nb-1)
- *   merge != 0 also performs the per-object atomicMax of the bids (:375-385);  iters >= 1 timed launches, with an L2
+ *   merge bit 0: also perform the per-object atomicMax of the bids (:375-385); bit 1: disable the bound pruning of
+ *   the price gathers (A/B measurement);  iters >= 1 timed launches, with an L2
  *   flush (a write larger than L2) before each when flush_l2 != 0.
  *   jbest_out / bid_out (nb, host, may be NULL); *avg_ms_out = mean device time of one launch (CUDA events).
  */

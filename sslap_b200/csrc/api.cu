@@ -24,6 +24,7 @@ cudaError_t sslapb_launch_dense_fill(const double *, int, int, int, const long l
 cudaError_t sslapb_launch_auction(const SslapbAuctionParams *, int, cudaStream_t);
 cudaError_t sslapb_auction_grid_size(int, int *);
 cudaError_t sslapb_launch_bid_sweep(const SslapbAuctionParams *, const int *, int, float, int, int, cudaStream_t);
+cudaError_t sslapb_launch_price_bounds(const SslapbAuctionParams *, cudaStream_t);
 cudaError_t sslapb_hk_launch_greedy(const long long *, const int *, int, int *, int *, SslapbHkFlags *, int, cudaStream_t);
 cudaError_t sslapb_hk_launch_phase_init(int, int, const int *, int *, int *, SslapbHkFlags *, int, cudaStream_t);
 cudaError_t sslapb_hk_launch_bfs_level(const long long *, const int *, int, int, const int *, int *, SslapbHkFlags *, int,
@@ -332,6 +333,9 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
     SslapbCtrl c;
     memset(&c, 0, sizeof c);
     c.nu = N; c.eps = eps; c.target_eps = target; c.theta = 0.15f; c.max_iter = max_iter; c.ece_final = -1;
+    c.pmin_key[0] = 0x8000000000000000ull;                     // all prices start at +0.0 (auction_.pyx:220)
+    c.pmin_key[1] = ~0ull;
+    c.pmax_key = 0x8000000000000000ull;
     CK(cudaMemcpyAsync(P.ctrl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->ev[3], h->stream));
     CK(sslapb_launch_auction(&P, h->grid, h->stream));
@@ -370,6 +374,7 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
         for (int k = 0; k < 8; ++k) meta->prof_ms[k] = (float)((double)c.prof[k] * 1e-6);
         if (getenv("SSLAPB_PRINT_PROF2")) { fprintf(stderr, "prof2:"); for (int k = 0; k < 8; ++k) fprintf(stderr, " %llu", c.prof2[k]); fprintf(stderr, "\n"); }
         meta->stop_reason = c.done;
+        meta->prune_second_pass = c.prune_second_pass;
         (void)assigned;
     }
     return SSLAPB_OK;
@@ -498,6 +503,7 @@ extern "C" int sslapb_bid_sweep(sslapb_handle *h, const double *prices, const in
         d_bidders = h->bidders.as<int>();
         if ((size_t)nb > (size_t)h->N) { CK(h->bidj.reserve((size_t)nb * 4)); CK(h->bidv.reserve((size_t)nb * 8)); P.bidj = h->bidj.as<int>(); P.bidv = h->bidv.as<double>(); }
     }
+    CK(sslapb_launch_price_bounds(&P, h->stream));
     const size_t flush_bytes = (size_t)256 << 20;
     if (flush_l2) CK(h->flush.reserve(flush_bytes));
     float total = 0.f;

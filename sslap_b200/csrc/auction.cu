@@ -30,6 +30,7 @@ __device__ __forceinline__ long long sslapb_clk_after(int dep)
 #else
 #define SSLAPB_PROBE(K_, DEP_) do { } while (0)
 #endif
+#define SSLAPB_SWEEP_THREADS 768 // stand-alone sweep: 24 warps per SM, 85 registers each (two rows in flight per warp)
 #define SSLAPB_THREADS 512       // persistent kernel: one CTA of 16 warps per SM (128 registers per thread)
 
 // ----------------------------------------------------------------------------------------------------------------------
@@ -175,6 +176,147 @@ __device__ __forceinline__ SslapbBid row_bid_core(const int *__restrict__ cols, 
     return o;
 }
 
+// Bound-pruned sweep of one row that fits a single warp pass (grid regime).  Exact, but most price gathers are skipped:
+//   v_k = a_k - p_k <= a_k - L for any lower bound L of the prices, so an entry whose bound a_k - L is strictly below the
+//   second-best value found among the gathered entries can be neither the best nor the second best.
+// Pass 1 gathers the entries within `spread` (current price range, a heuristic) of the row's largest a_k; the bound test
+// then either proves the rest irrelevant (usual case) or names the entries to gather in pass 2 (after which no further
+// violation is possible because the second-best value only grows).  The random price gathers are what limits the
+// sweep (one L1TEX wavefront and one 32-byte L2 sector per 8-byte price), not the 12 B/entry stream.
+struct SslapbStreamChunk { int4 cj; double2 va, vb; };
+__device__ __forceinline__ SslapbStreamChunk sslapb_stream_chunk(const int *__restrict__ cols,
+                                                                 const double *__restrict__ vals, long long start,
+                                                                 long long end, int lane)
+{
+    SslapbStreamChunk c;
+    c.cj = make_int4(0, 0, 0, 0); c.va = make_double2(0.0, 0.0); c.vb = c.va;
+    const long long ch = (start >> 2) + lane;
+    if (ch < ((end + 3) >> 2)) {
+        c.cj = sslapb_ldg_stream_i4(reinterpret_cast<const int4 *>(cols) + ch);
+        c.va = sslapb_ldg_stream_d2(reinterpret_cast<const double2 *>(vals) + 2 * ch);
+        c.vb = sslapb_ldg_stream_d2(reinterpret_cast<const double2 *>(vals) + 2 * ch + 1);
+    }
+    return c;
+}
+
+// Top-2 of four values by a two-level tournament in float64 (the later slot wins equal values: "last maximal entry",
+// auction_.pyx:351; -0.0 == +0.0 exactly as in the reference).  Absent slots carry -inf.
+struct SslapbLaneTop { double b, s; int w; };
+__device__ __forceinline__ SslapbLaneTop sslapb_lane_top2(double v0, double v1, double v2, double v3)
+{
+    const bool t01 = v1 >= v0, t23 = v3 >= v2;
+    const double b01 = t01 ? v1 : v0, l01 = t01 ? v0 : v1;
+    const double b23 = t23 ? v3 : v2, l23 = t23 ? v2 : v3;
+    const bool tf = b23 >= b01;
+    SslapbLaneTop r;
+    r.b = tf ? b23 : b01;
+    const double x = tf ? b01 : b23, y = tf ? l23 : l01;
+    r.s = x > y ? x : y;
+    r.w = tf ? (t23 ? 3 : 2) : (t01 ? 1 : 0);
+    return r;
+}
+
+// order-preserving key with -0.0 folded into +0.0 (cross-lane ties must behave like the float compare)
+__device__ __forceinline__ unsigned long long sslapb_key_of(double v)
+{
+    long long bits = __double_as_longlong(v);
+    if ((bits << 1) == 0) bits = 0;
+    return (unsigned long long)(bits ^ ((bits >> 63) | (long long)0x8000000000000000ull));
+}
+
+__device__ __forceinline__ float sslapb_redux_max_f32(float v)
+{
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// Cross-lane part shared by the single-pass sweeps: lexicographic maximum of (value, row index) and the second largest
+// value of the row, from each lane's (best, second, index) — five REDUX on the integer images of the values.
+struct SslapbRowTop { bool iswin; unsigned own; unsigned long long skey; };
+__device__ __forceinline__ SslapbRowTop sslapb_row_top2(double b, double s, int bi)
+{
+    const unsigned long long bk = bi >= 0 ? sslapb_key_of(b) : 0ull;
+    const unsigned long long sk = bi >= 0 ? sslapb_key_of(s) : 0ull;
+    const unsigned bh = (unsigned)(bk >> 32), bl = (unsigned)bk;
+    const unsigned khi = __reduce_max_sync(SSLAPB_FULL, bh);
+    const unsigned klo = __reduce_max_sync(SSLAPB_FULL, bh == khi ? bl : 0u);
+    const bool top = (bh == khi) & (bl == klo);
+    const int widx = __reduce_max_sync(SSLAPB_FULL, top ? bi : -1);
+    SslapbRowTop r;
+    r.iswin = top & (bi == widx) & (bi >= 0);
+    const unsigned long long cand = r.iswin ? sk : bk;
+    const unsigned chh = (unsigned)(cand >> 32), chl = (unsigned)cand;
+    const unsigned shi = __reduce_max_sync(SSLAPB_FULL, chh);
+    const unsigned slo = __reduce_max_sync(SSLAPB_FULL, chh == shi ? chl : 0u);
+    r.skey = ((unsigned long long)shi << 32) | slo;
+    r.own = __ballot_sync(SSLAPB_FULL, r.iswin);
+    return r;
+}
+// key of "-inf": a second-best key at or below it means the row has no second entry (w_i = -inf, auction_.pyx:344)
+#define SSLAPB_KEY_NEG_INF 0x000fffffffffffffull
+
+// Bound-pruned sweep of one row that fits a single warp pass (grid regime).  Exact, but most price gathers are skipped:
+//   v_k = a_k - p_k <= a_k - L for any lower bound L of the prices, so an entry whose bound a_k - L is strictly below the
+//   second-best value found among the gathered entries can be neither the best nor the second best.
+// Pass 1 gathers the entries within `spread` (current price range — a heuristic, evaluated in float32) of the row's
+// largest a_k; the float64 bound test then either proves the rest irrelevant (usual case) or names the entries to gather
+// in pass 2 (after which no further violation is possible because the second-best value only grows).
+// Entries of the chunk that belong to neighbouring rows are replaced by a = -inf up front.
+__device__ __forceinline__ SslapbBid row_bid_pruned(const SslapbStreamChunk &C, const double *price, long long start,
+                                                    long long end, int lane, double eps, double pmin, float spread,
+                                                    int &second_pass)
+{
+    const long long ch = (start >> 2) + lane;
+    const int off = (int)((ch << 2) - start);                 // row index of slot 0 (may be negative)
+    const int deg = (int)(end - start);
+    const int4 cj = C.cj;
+    const bool m0 = (unsigned)off < (unsigned)deg, m1 = (unsigned)(off + 1) < (unsigned)deg;
+    const bool m2 = (unsigned)(off + 2) < (unsigned)deg, m3 = (unsigned)(off + 3) < (unsigned)deg;
+    const double a0 = m0 ? C.va.x : SSLAPB_NEG_INF, a1 = m1 ? C.va.y : SSLAPB_NEG_INF;
+    const double a2 = m2 ? C.vb.x : SSLAPB_NEG_INF, a3 = m3 ? C.vb.y : SSLAPB_NEG_INF;
+    // heuristic gather set (float32, rounded towards gathering more)
+    const float f0 = __double2float_ru(a0), f1 = __double2float_ru(a1), f2 = __double2float_ru(a2), f3 = __double2float_ru(a3);
+    const float fmx = sslapb_redux_max_f32(fmaxf(fmaxf(f0, f1), fmaxf(f2, f3)));
+    const float thr = fmx - spread - 1e-3f * fabsf(fmx);
+    bool g0 = f0 >= thr, g1 = f1 >= thr, g2 = f2 >= thr, g3 = f3 >= thr;   // -inf (absent) is never gathered
+    double v0 = SSLAPB_NEG_INF, v1 = SSLAPB_NEG_INF, v2 = SSLAPB_NEG_INF, v3 = SSLAPB_NEG_INF;
+    if (g0) v0 = a0 - price[cj.x];
+    if (g1) v1 = a1 - price[cj.y];
+    if (g2) v2 = a2 - price[cj.z];
+    if (g3) v3 = a3 - price[cj.w];
+    SslapbLaneTop lt = sslapb_lane_top2(v0, v1, v2, v3);
+    bool mw = (lt.w & 2) ? ((lt.w & 1) ? g3 : g2) : ((lt.w & 1) ? g1 : g0);
+    SslapbRowTop rt = sslapb_row_top2(lt.b, lt.s, (mw && (unsigned)(off + lt.w) < (unsigned)deg) ? off + lt.w : -1);
+    {
+        // exactness test for the entries not gathered: is a_k - L (>= v_k) still strictly below the second-best value?
+        const double sval = rt.skey > SSLAPB_KEY_NEG_INF ? sslapb_key2double(rt.skey) : SSLAPB_NEG_INF;
+        const bool x0 = m0 && !g0 && !((a0 - pmin) < sval), x1 = m1 && !g1 && !((a1 - pmin) < sval);
+        const bool x2 = m2 && !g2 && !((a2 - pmin) < sval), x3 = m3 && !g3 && !((a3 - pmin) < sval);
+        if (__any_sync(SSLAPB_FULL, x0 | x1 | x2 | x3)) {
+            ++second_pass;
+            if (x0) { v0 = a0 - price[cj.x]; g0 = true; }
+            if (x1) { v1 = a1 - price[cj.y]; g1 = true; }
+            if (x2) { v2 = a2 - price[cj.z]; g2 = true; }
+            if (x3) { v3 = a3 - price[cj.w]; g3 = true; }
+            lt = sslapb_lane_top2(v0, v1, v2, v3);
+            mw = (lt.w & 2) ? ((lt.w & 1) ? g3 : g2) : ((lt.w & 1) ? g1 : g0);
+            rt = sslapb_row_top2(lt.b, lt.s, (mw && (unsigned)(off + lt.w) < (unsigned)deg) ? off + lt.w : -1);
+        }
+    }
+    const int src = rt.own ? (__ffs(rt.own) - 1) : lane;
+    const double myc = (lt.w & 2) ? ((lt.w & 1) ? a3 : a2) : ((lt.w & 1) ? a1 : a0);
+    const int myj = (lt.w & 2) ? ((lt.w & 1) ? cj.w : cj.z) : ((lt.w & 1) ? cj.y : cj.x);
+    const double bc = __shfl_sync(SSLAPB_FULL, myc, src);
+    const int bj = __shfl_sync(SSLAPB_FULL, myj, src);
+    SslapbBid o;
+    o.j = rt.own ? bj : -1;
+    o.powner = -1; o.pdeg = 0; o.pstart = 0;
+    const double wi = rt.skey > SSLAPB_KEY_NEG_INF ? sslapb_key2double(rt.skey) : SSLAPB_NEG_INF;   // :344
+    o.bid = (bc - wi) + eps;                                   // :360
+    return o;
+}
+
 template <int W>
 __device__ __forceinline__ void row_bid(const int *__restrict__ cols, const double *__restrict__ vals,
                                         const double *price, long long start, long long end, int t, double eps,
@@ -185,12 +327,66 @@ __device__ __forceinline__ void row_bid(const int *__restrict__ cols, const doub
     bid = o.bid;
 }
 
+// Out of line on purpose: the warp-list loops are executed by one to a few warps, so their speed is set by instruction
+// fetch as much as by memory; keeping the rare long-row sweep out of the loop bodies keeps those bodies inside the
+// instruction cache's first level.
 template <int W>
-__device__ __forceinline__ SslapbBid row_bid_rec(const int *__restrict__ cols, const double *__restrict__ vals,
-                                                 const SslapbObjRec *rec, long long start, long long end, int t,
-                                                 double eps, long long *acc = nullptr)
+__device__ __noinline__ SslapbBid row_bid_rec(const int *__restrict__ cols, const double *__restrict__ vals,
+                                              const SslapbObjRec *rec, long long start, long long end, int t,
+                                              double eps, long long *acc = nullptr)
 {
     return row_bid_core<W, true>(cols, vals, nullptr, rec, start, end, t, eps, acc);
+}
+
+// Bidding step of the grid regime over list positions a = first, first+stride, ... < nb, software-pipelined inside every
+// warp: while row m is being processed (price gathers + top-2), the entries of row m+1 are already in flight, the row
+// offsets of row m+2 are being fetched and the person of position m+3 is being read.  Without this the sweep is a
+// chain of four dependent round trips per row per warp and runs at ~30 % of the HBM roofline regardless of the
+// number of gathers.  `persons` = NULL means position == person (full frontier).
+template <typename Emit>
+__device__ __forceinline__ void sweep_positions(const SslapbAuctionParams &P, int *persons, const int *mover, int nb,
+                                                int first, int stride, int lane, double eps, double pmin, float spread,
+                                                bool prune, int &second_pass, Emit emit)
+{
+    if (first >= nb) return;
+    // pipeline registers: person ids two and three positions ahead, row offsets one and two ahead, entries one ahead
+    auto person_at = [&](int a) -> int { return (a < nb) ? (persons ? persons[a] : a) : -1; };
+    auto decode = [&](int a, int v) -> int {                  // rank-encoded hole left by the previous compaction
+        if (v < -1) { v = mover[-(v + 2)]; if (lane == 0) persons[a] = v; }
+        return v;
+    };
+    int a0 = first;
+    int v0 = decode(a0, person_at(a0));
+    int v1 = person_at(a0 + stride);
+    int v2 = person_at(a0 + 2 * stride);
+    long long st0 = __ldg(P.rowptr + v0), en0 = __ldg(P.rowptr + v0 + 1);
+    v1 = (a0 + stride < nb) ? decode(a0 + stride, v1) : -1;
+    long long st1 = 0, en1 = 0;
+    if (v1 >= 0) { st1 = __ldg(P.rowptr + v1); en1 = __ldg(P.rowptr + v1 + 1); }
+    SslapbStreamChunk c0 = sslapb_stream_chunk(P.cols, P.vals, st0, en0, lane);
+    for (;;) {
+        const int a1 = a0 + stride, a2 = a0 + 2 * stride, a3 = a0 + 3 * stride;
+        // stage A: person of position m+3
+        const int v3 = person_at(a3);
+        // stage B: row offsets of position m+2
+        long long st2 = 0, en2 = 0;
+        if (a2 < nb) { v2 = decode(a2, v2); st2 = __ldg(P.rowptr + v2); en2 = __ldg(P.rowptr + v2 + 1); }
+        // stage C: entries of position m+1
+        SslapbStreamChunk c1;
+        c1.cj = make_int4(0, 0, 0, 0); c1.va = make_double2(0.0, 0.0); c1.vb = c1.va;
+        if (a1 < nb) c1 = sslapb_stream_chunk(P.cols, P.vals, st1, en1, lane);
+        // stage D: process position m
+        int j; double bid;
+        if (prune && (((en0 + 3) >> 2) - (st0 >> 2)) <= 32) {
+            const SslapbBid o = row_bid_pruned(c0, P.price, st0, en0, lane, eps, pmin, spread, second_pass);
+            j = o.j; bid = o.bid;
+        } else {
+            row_bid<32>(P.cols, P.vals, P.price, st0, en0, lane, eps, j, bid);
+        }
+        emit(a0, j, bid);
+        if (a1 >= nb) break;
+        a0 = a1; st0 = st1; en0 = en1; c0 = c1; st1 = st2; en1 = en2; v2 = v3;
+    }
 }
 
 // eCE / objective sweep of one row by a full warp (auction_.pyx:460-483 and :504-521).
@@ -343,105 +539,223 @@ __device__ __forceinline__ SslapbChunk sslapb_load_chunk(const int *__restrict__
     return c;
 }
 
+// One bidder whose row fits a single warp pass (<= 32 aligned chunks, i.e. up to 125..128 entries), row entries already
+// in registers (`cur`).  Gathers the object records, finds the winning entry (3 REDUX) and — before finishing the bid —
+// requests the row of the object's current owner (`nxt`), the person who bids next if this bid wins.  The second-best
+// reduction and the bid arithmetic overlap that load.  Returns false for an empty row.
+__device__ __forceinline__ bool sweep_single(const SslapbAuctionParams &P, const SslapbChunk &cur, long long st, int dg,
+                                             double eps, bool want_next, SslapbBid &B, SslapbChunk &nxt, bool &nxt_single)
+{
+    const int lane = threadIdx.x & 31;
+    const long long ch = (st >> 2) + lane;
+    const int off = (int)((ch << 2) - st);                    // row index of slot 0 (may be negative)
+    const bool m0 = (unsigned)off < (unsigned)dg, m1 = (unsigned)(off + 1) < (unsigned)dg;
+    const bool m2 = (unsigned)(off + 2) < (unsigned)dg, m3 = (unsigned)(off + 3) < (unsigned)dg;
+    const int4 cj = cur.cj;
+    SslapbRec256 q0, q1, q2, q3;
+    q0.start = q1.start = q2.start = q3.start = 0ull;
+    q0.owner_deg = q1.owner_deg = q2.owner_deg = q3.owner_deg = 0xffffffffull;      // owner = -1, deg = 0
+    q0.price_bits = q1.price_bits = q2.price_bits = q3.price_bits = 0ull;
+    if (m0) q0 = sslapb_ld_rec256(P.rec + cj.x);
+    if (m1) q1 = sslapb_ld_rec256(P.rec + cj.y);
+    if (m2) q2 = sslapb_ld_rec256(P.rec + cj.z);
+    if (m3) q3 = sslapb_ld_rec256(P.rec + cj.w);
+    // a_ij - p_j in float64 as the reference; slots of neighbouring rows carry -inf
+    const double v0 = m0 ? cur.va.x - __longlong_as_double((long long)q0.price_bits) : SSLAPB_NEG_INF;
+    const double v1 = m1 ? cur.va.y - __longlong_as_double((long long)q1.price_bits) : SSLAPB_NEG_INF;
+    const double v2 = m2 ? cur.vb.x - __longlong_as_double((long long)q2.price_bits) : SSLAPB_NEG_INF;
+    const double v3 = m3 ? cur.vb.y - __longlong_as_double((long long)q3.price_bits) : SSLAPB_NEG_INF;
+    const SslapbLaneTop lt = sslapb_lane_top2(v0, v1, v2, v3);
+    const int bi = ((unsigned)(off + lt.w) < (unsigned)dg) ? off + lt.w : -1;
+    const unsigned long long qs = (lt.w & 2) ? ((lt.w & 1) ? q3.start : q2.start) : ((lt.w & 1) ? q1.start : q0.start);
+    const unsigned long long qo = (lt.w & 2) ? ((lt.w & 1) ? q3.owner_deg : q2.owner_deg) : ((lt.w & 1) ? q1.owner_deg : q0.owner_deg);
+    // top-1 across the warp -> whose object -> request the owner's row right away
+    const unsigned long long bk = bi >= 0 ? sslapb_key_of(lt.b) : 0ull;
+    const unsigned bh = (unsigned)(bk >> 32), bl = (unsigned)bk;
+    const unsigned khi = __reduce_max_sync(SSLAPB_FULL, bh);
+    const unsigned klo = __reduce_max_sync(SSLAPB_FULL, bh == khi ? bl : 0u);
+    const bool top = (bh == khi) & (bl == klo);
+    const int widx = __reduce_max_sync(SSLAPB_FULL, top ? bi : -1);
+    const bool iswin = top & (bi == widx) & (bi >= 0);
+    const unsigned own = __ballot_sync(SSLAPB_FULL, iswin);
+    if (own == 0u) return false;
+    const int src = __ffs(own) - 1;
+    const unsigned long long wo = __shfl_sync(SSLAPB_FULL, qo, src);
+    B.pstart = (long long)__shfl_sync(SSLAPB_FULL, qs, src);
+    B.powner = (int)(unsigned)wo;
+    B.pdeg = (int)(wo >> 32);
+    const long long n0 = B.pstart >> 2, n1 = (B.pstart + B.pdeg + 3) >> 2;
+    nxt_single = (n1 - n0) <= 32;
+    nxt = sslapb_load_chunk(P.cols, P.vals, n0 + lane, want_next && B.powner >= 0 && nxt_single && (n0 + lane < n1));
+    // ---- everything below overlaps the load above
+    const unsigned long long sk = bi >= 0 ? sslapb_key_of(lt.s) : 0ull;
+    const unsigned long long cand = iswin ? sk : bk;
+    const unsigned chh = (unsigned)(cand >> 32), chl = (unsigned)cand;
+    const unsigned shi = __reduce_max_sync(SSLAPB_FULL, chh);
+    const unsigned slo = __reduce_max_sync(SSLAPB_FULL, chh == shi ? chl : 0u);
+    const unsigned long long skey = ((unsigned long long)shi << 32) | slo;
+    const double myc = (lt.w & 2) ? ((lt.w & 1) ? cur.vb.y : cur.vb.x) : ((lt.w & 1) ? cur.va.y : cur.va.x);
+    const int myj = (lt.w & 2) ? ((lt.w & 1) ? cj.w : cj.z) : ((lt.w & 1) ? cj.y : cj.x);
+    const double bc = __shfl_sync(SSLAPB_FULL, myc, src);
+    B.j = __shfl_sync(SSLAPB_FULL, myj, src);
+    const double wi = skey > SSLAPB_KEY_NEG_INF ? sslapb_key2double(skey) : SSLAPB_NEG_INF;   // :344
+    B.bid = (bc - wi) + eps;                                   // :360
+    return true;
+}
+
+// The winner's writes (auction_.pyx:397-418) — executed by one lane.
+__device__ __forceinline__ void commit_win(const SslapbAuctionParams &P, int person, long long st, int dg, const SslapbBid &B)
+{
+    SslapbObjRec r;
+    r.start = st; r.owner = person; r.deg = dg; r.price = B.bid; r.pad = 0;
+    *reinterpret_cast<int4 *>(P.rec + B.j) = *reinterpret_cast<const int4 *>(&r);        // owner + its row (:418)
+    P.rec[B.j].price = B.bid;                                  // :397
+    P.price[B.j] = B.bid;
+    P.p2o[person] = B.j;                                       // :417
+    if (B.powner >= 0) P.p2o[B.powner] = -1;                   // :404
+}
+
 // Single-bidder chain (52 % of all rounds at N = 100k): person i bids, wins (there is no competitor), evicts the owner i'
-// of the object, i' bids, ...  One warp, no barrier.  Software-pipelined: as soon as the winning entry is known (3 REDUX
-// after the record gather) the evicted owner's row is requested; the second-best reduction, the bid arithmetic and the
-// stores of the current round overlap that load.  Dependent chain per round = row entries -> object records -> top-1.
-// Rows longer than one warp pass (> 125 entries) take the generic path.  Returns the new count (0 or 1).
+// of the object, i' bids, ...  One warp, no barrier; dependent chain per round = row entries -> object records -> top-1
+// (see sweep_single).  Rows longer than one warp pass take the generic sweep.  Returns the new count (0 or 1).
 __device__ __forceinline__ int chain_rounds(const SslapbAuctionParams &P, double eps, int &li, long long &lst, int &ldg,
                                             long long &its, long long max_iter, int &done, long long &rounds)
 {
     const int lane = threadIdx.x & 31;
     li = __shfl_sync(SSLAPB_FULL, li, 0); lst = __shfl_sync(SSLAPB_FULL, lst, 0); ldg = __shfl_sync(SSLAPB_FULL, ldg, 0);
     int nu = 1;
-    long long c0 = lst >> 2, c1 = (lst + ldg + 3) >> 2;
-    bool single = (c1 - c0) <= 32;
-    SslapbChunk cur = sslapb_load_chunk(P.cols, P.vals, c0 + lane, single && (c0 + lane < c1));
+    bool single = (((lst + ldg + 3) >> 2) - (lst >> 2)) <= 32;
+    SslapbChunk cur = sslapb_load_chunk(P.cols, P.vals, (lst >> 2) + lane, single && ((lst >> 2) + lane < ((lst + ldg + 3) >> 2)));
     while (nu == 1 && !done) {
         SslapbBid B;
-        if (!single) {                                         // long row: generic sweep, nothing prefetched
+        SslapbChunk nxt;
+        bool nsingle = false;
+        if (single) {
+            if (!sweep_single(P, cur, lst, ldg, eps, its + 1 < max_iter, B, nxt, nsingle)) { done = 4; break; }
+        } else {                                               // long row: generic sweep, nothing prefetched
             B = row_bid_rec<32>(P.cols, P.vals, P.rec, lst, lst + ldg, lane, eps);
-            nu = warp_resolve(P, 1, li, lst, ldg, B);
-            li = __shfl_sync(SSLAPB_FULL, li, 0); lst = __shfl_sync(SSLAPB_FULL, lst, 0); ldg = __shfl_sync(SSLAPB_FULL, ldg, 0);
-            ++its; ++rounds;
-            if (its >= max_iter) done = 3;
-            if (nu == 1) {
-                c0 = lst >> 2; c1 = (lst + ldg + 3) >> 2; single = (c1 - c0) <= 32;
-                cur = sslapb_load_chunk(P.cols, P.vals, c0 + lane, single && (c0 + lane < c1));
-            }
-            continue;
+            if (B.j < 0) { done = 4; break; }
+            const long long n0 = B.pstart >> 2, n1 = (B.pstart + B.pdeg + 3) >> 2;
+            nsingle = (n1 - n0) <= 32;
+            nxt = sslapb_load_chunk(P.cols, P.vals, n0 + lane, B.powner >= 0 && nsingle && (n0 + lane < n1));
         }
-        const long long ch = c0 + lane;
-        const bool active = ch < c1;
-        const int lo = (int)(lst - (ch << 2)), hi = active ? (int)min(lst + ldg - (ch << 2), 4ll) : 0;
-        const bool m0 = (0 >= lo) & (0 < hi), m1 = (1 >= lo) & (1 < hi), m2 = (2 >= lo) & (2 < hi), m3 = (3 >= lo) & (3 < hi);
-        const int4 cj = cur.cj;
-        const int4 z = make_int4(0, 0, -1, 0);
-        const int4 r0 = m0 ? *reinterpret_cast<const int4 *>(P.rec + cj.x) : z;
-        const int4 r1 = m1 ? *reinterpret_cast<const int4 *>(P.rec + cj.y) : z;
-        const int4 r2 = m2 ? *reinterpret_cast<const int4 *>(P.rec + cj.z) : z;
-        const int4 r3 = m3 ? *reinterpret_cast<const int4 *>(P.rec + cj.w) : z;
-        const double p0 = m0 ? P.rec[cj.x].price : 0.0;
-        const double p1 = m1 ? P.rec[cj.y].price : 0.0;
-        const double p2 = m2 ? P.rec[cj.z].price : 0.0;
-        const double p3 = m3 ? P.rec[cj.w].price : 0.0;
-        const unsigned long long k0 = sslapb_vkey(cur.va.x, p0, m0), k1 = sslapb_vkey(cur.va.y, p1, m1);
-        const unsigned long long k2 = sslapb_vkey(cur.vb.x, p2, m2), k3 = sslapb_vkey(cur.vb.y, p3, m3);
-        const bool w01 = k1 >= k0, w23 = k3 >= k2;
-        const unsigned long long b01 = w01 ? k1 : k0, l01 = w01 ? k0 : k1;
-        const unsigned long long b23 = w23 ? k3 : k2, l23 = w23 ? k2 : k3;
-        const bool wf = b23 >= b01;
-        const unsigned long long b = wf ? b23 : b01;
-        const unsigned long long s = wf ? (b01 > l23 ? b01 : l23) : (b23 > l01 ? b23 : l01);
-        const int w4 = wf ? (w23 ? 3 : 2) : (w01 ? 1 : 0);
-        const int bi = b ? (int)((ch << 2) - lst) + w4 : -1;
-        const int4 br = (w4 & 2) ? ((w4 & 1) ? r3 : r2) : ((w4 & 1) ? r1 : r0);
-        // top-1 across the warp -> who is evicted -> request its row right away
-        const unsigned bh = (unsigned)(b >> 32), bl = (unsigned)b;
-        const unsigned khi = __reduce_max_sync(SSLAPB_FULL, bh);
-        const unsigned klo = __reduce_max_sync(SSLAPB_FULL, bh == khi ? bl : 0u);
-        const bool top = (bh == khi) & (bl == klo);
-        const int widx = __reduce_max_sync(SSLAPB_FULL, top ? bi : -1);
-        const bool iswin = top & (bi == widx) & (bi >= 0);
-        const unsigned own = __ballot_sync(SSLAPB_FULL, iswin);
-        if (own == 0u) { done = 4; break; }                    // empty row: cannot happen (rejected at CSR build)
-        const int src = __ffs(own) - 1;
-        const int powner = __shfl_sync(SSLAPB_FULL, br.z, src);
-        const int pdeg = __shfl_sync(SSLAPB_FULL, br.w, src);
-        const int sx = __shfl_sync(SSLAPB_FULL, br.x, src), sy = __shfl_sync(SSLAPB_FULL, br.y, src);
-        const long long pstart = (long long)(((unsigned long long)(unsigned)sy << 32) | (unsigned)sx);
-        const bool more = (powner >= 0) && (its + 1 < max_iter);
-        const long long n0 = pstart >> 2, n1 = (pstart + pdeg + 3) >> 2;
-        const bool nsingle = (n1 - n0) <= 32;
-        const SslapbChunk nxt = sslapb_load_chunk(P.cols, P.vals, n0 + lane, more && nsingle && (n0 + lane < n1));
-        // ---- the rest of this round overlaps the load above
-        const unsigned long long cand = iswin ? s : b;
-        const unsigned chh = (unsigned)(cand >> 32), chl = (unsigned)cand;
-        const unsigned shi = __reduce_max_sync(SSLAPB_FULL, chh);
-        const unsigned slo = __reduce_max_sync(SSLAPB_FULL, chh == shi ? chl : 0u);
-        const unsigned long long skey = ((unsigned long long)shi << 32) | slo;
-        const double myc = (w4 & 2) ? ((w4 & 1) ? cur.vb.y : cur.vb.x) : ((w4 & 1) ? cur.va.y : cur.va.x);
-        const int myj = (w4 & 2) ? ((w4 & 1) ? cj.w : cj.z) : ((w4 & 1) ? cj.y : cj.x);
-        const double bc = __shfl_sync(SSLAPB_FULL, myc, src);
-        const int j = __shfl_sync(SSLAPB_FULL, myj, src);
-        const double wi = skey ? sslapb_key2double(skey) : SSLAPB_NEG_INF;
-        const double bid = (bc - wi) + eps;                    // :360
-        if (lane == 0) {                                       // the only bidder wins (:379-385, :394-427)
-            SslapbObjRec r;
-            r.start = lst; r.owner = li; r.deg = ldg; r.price = bid; r.pad = 0;
-            *reinterpret_cast<int4 *>(P.rec + j) = *reinterpret_cast<const int4 *>(&r);
-            P.rec[j].price = bid;
-            P.price[j] = bid;
-            P.p2o[li] = j;
-            if (powner >= 0) P.p2o[powner] = -1;
-        }
+        if (lane == 0) commit_win(P, li, lst, ldg, B);         // the only bidder wins (:379-385, :394-427)
         __syncwarp();
         ++its; ++rounds;
         if (its >= max_iter) done = 3;
-        if (powner < 0) { nu = 0; li = -1; break; }            // nobody evicted: the frontier is empty
-        li = powner; lst = pstart; ldg = pdeg;                 // the evicted owner is the next (and only) bidder
-        c0 = n0; c1 = n1; single = nsingle; cur = nxt;
+        if (B.powner < 0) { nu = 0; li = -1; break; }          // nobody evicted: the frontier is empty
+        li = B.powner; lst = B.pstart; ldg = B.pdeg;           // the evicted owner is the next (and only) bidder
+        single = nsingle; cur = nxt;
     }
+    return nu;
+}
+
+// 2..16 bidders: warp a owns list position a for as long as the frontier stays this small.  Per round every active
+// warp sweeps its bidder (row entries usually already in registers: the next occupant of a slot is either the same
+// person — it lost — or the owner it evicted, whose row was requested during the sweep), publishes (object, bid), and
+// after one barrier decides by itself whether it won (no serial merge); winners commit; after a second barrier every
+// warp derives the compacted list (push_all_left, auction_.pyx:137-162) redundantly from shared memory.
+__device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double eps, int nu, int *s_list,
+                                            long long *s_start, int *s_deg, int *s_j, double *s_bidv, long long &its,
+                                            long long max_iter, int &done, long long &rounds, int &me, long long &st,
+                                            int &dg)
+{
+    const int lane = threadIdx.x & 31, a = __shfl_sync(SSLAPB_FULL, (int)(threadIdx.x >> 5), 0);
+    bool active = a < nu;
+    bool single = false;
+    SslapbChunk cur;
+    cur.cj = make_int4(0, 0, 0, 0); cur.va = make_double2(0.0, 0.0); cur.vb = cur.va;
+    me = -1; st = 0; dg = 0;
+    if (active) {
+        me = s_list[a]; st = s_start[a]; dg = s_deg[a];
+        single = (((st + dg + 3) >> 2) - (st >> 2)) <= 32;
+        cur = sslapb_load_chunk(P.cols, P.vals, (st >> 2) + lane, single && ((st >> 2) + lane < ((st + dg + 3) >> 2)));
+    }
+#ifdef SSLAPB_PROFILE_SOLO
+    long long pq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define MQ(K_, DEP_) do { const long long t_ = sslapb_clk_after((int)(DEP_)); pq[K_] += t_ - tq; tq = t_; } while (0)
+    long long tq = sslapb_clk_after(nu);
+#else
+#define MQ(K_, DEP_) do { } while (0)
+#endif
+    while (nu > 1 && nu <= SSLAPB_THREADS / 32 && !done) {
+        SslapbBid B;
+        B.j = -1; B.bid = 0.0; B.powner = -1; B.pdeg = 0; B.pstart = 0;
+        SslapbChunk nxt = cur;
+        bool nsingle = false;
+        if (active) {
+            bool ok;
+            if (single) {
+                ok = sweep_single(P, cur, st, dg, eps, true, B, nxt, nsingle);
+            } else {
+                B = row_bid_rec<32>(P.cols, P.vals, P.rec, st, st + dg, lane, eps);
+                ok = B.j >= 0;
+                const long long n0 = B.pstart >> 2, n1 = (B.pstart + B.pdeg + 3) >> 2;
+                nsingle = (n1 - n0) <= 32;
+                nxt = sslapb_load_chunk(P.cols, P.vals, n0 + lane, ok && B.powner >= 0 && nsingle && (n0 + lane < n1));
+            }
+            if (!ok) { B.j = -1; done = 4; }
+            if (lane == 0) { s_j[a] = B.j; s_bidv[a] = B.bid; }
+        }
+        MQ(0, B.j ^ __double2hiint(B.bid) ^ B.powner);
+        __syncthreads();
+        MQ(1, s_j[lane & 15]);
+        int nme = me; long long nst = st; int ndg = dg; bool won = false;
+        if (active) {                                          // merge (:375-385): do I hold the best bid on my object?
+            const int oj = lane < nu ? s_j[lane] : -1;
+            const double ob = lane < nu ? s_bidv[lane] : 0.0;
+            const bool beaten = (lane < nu) && (lane != a) && (oj == B.j) && (ob > B.bid || (ob == B.bid && lane < a));
+            won = (B.j >= 0) && !__any_sync(SSLAPB_FULL, beaten);
+            if (won) {
+                if (lane == 0) commit_win(P, me, st, dg, B);
+                nme = B.powner; nst = B.pstart; ndg = B.pdeg;  // evicted owner takes the slot (:409) or hole (:412)
+            }
+            if (lane == 0) { s_list[a] = nme; s_start[a] = nst; s_deg[a] = ndg; }
+        }
+        if (__any_sync(SSLAPB_FULL, lane < nu && s_j[lane] < 0)) done = 4;   // uniform across the CTA (same smem)
+        ++its; ++rounds;
+        if (its >= max_iter && !done) done = 3;
+        MQ(2, (int)won ^ nme ^ done);
+        __syncthreads();
+        MQ(3, s_list[lane & 15]);
+        // compaction (:429-430), identical in every warp
+        const int v = lane < nu ? s_list[lane] : 0;
+        const unsigned holes = __ballot_sync(SSLAPB_FULL, lane < nu && v < 0);
+        const int new_nu = nu - __popc(holes);
+        int src = a;
+        if (holes) {
+            const unsigned valid = (1u << nu) - 1u, leftm = (1u << new_nu) - 1u;
+            const unsigned left_holes = holes & leftm, right_live = valid & ~holes & ~leftm;
+            if (a < new_nu && ((left_holes >> a) & 1u)) {
+                unsigned m = right_live;
+                for (int q = __popc(left_holes & ((1u << a) - 1u)); q > 0; --q) m &= m - 1u;
+                src = __ffs(m) - 1;
+            }
+        }
+        const int old_me = me;
+        nu = new_nu;
+        active = a < nu;
+        if (active) {
+            if (src != a) { nme = s_list[src]; nst = s_start[src]; ndg = s_deg[src]; }
+            me = nme; st = nst; dg = ndg;
+            if (src == a && won) { cur = nxt; single = nsingle; }               // the evicted owner: row already requested
+            else if (src == a && me == old_me) { /* lost: same person, same row, still in registers */ }
+            else {
+                single = (((st + dg + 3) >> 2) - (st >> 2)) <= 32;
+                cur = sslapb_load_chunk(P.cols, P.vals, (st >> 2) + lane, single && ((st >> 2) + lane < ((st + dg + 3) >> 2)));
+            }
+        } else {
+            me = -1;
+        }
+        // no third barrier: s_list / s_j are rewritten only after the next round's first barrier / after this round's second
+        MQ(4, me ^ nu ^ cur.cj.x ^ __double2hiint(cur.vb.y));
+#ifdef SSLAPB_PROFILE_SOLO
+        pq[5] += 1; pq[6] += nu;
+#endif
+    }
+#ifdef SSLAPB_PROFILE_SOLO
+    if (threadIdx.x == 0) for (int k = 0; k < 8; ++k) P.ctrl->prof2[k] += (unsigned long long)pq[k];
+#endif
     return nu;
 }
 
@@ -449,8 +763,9 @@ __device__ __forceinline__ int chain_rounds(const SslapbAuctionParams &P, double
 __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, SslapbCtrl *C, int nu, float eps_f,
                                              long long its, long long max_iter)
 {
-    __shared__ int s_list[32], s_deg[32];
+    __shared__ int s_list[32], s_deg[32], s_j[32];
     __shared__ long long s_start[32];
+    __shared__ double s_bidv[32];
     __shared__ SslapbBid s_bid[32];
     __shared__ int s_nu, s_done;
     __shared__ long long s_its, s_rw, s_rs;
@@ -473,8 +788,8 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
     __syncthreads();
 
     unsigned long long tw0 = sslapb_globaltimer();
-    // ---- warp regime (2..32 bidders): one warp per bidder, 2 block barriers per round
-    while (nu > 1 && !done) {
+    // ---- 17..32 bidders: positions strided over the warps, warp 0 merges; 2 block barriers per round
+    while (nu > SSLAPB_THREADS / 32 && !done) {
         for (int a = warp; a < nu; a += SSLAPB_THREADS / 32) {
             const long long st = s_start[a];
             const SslapbBid b = row_bid_rec<32>(P.cols, P.vals, P.rec, st, st + s_deg[a], lane, eps);
@@ -494,15 +809,17 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
         nu = __shfl_sync(SSLAPB_FULL, s_nu, 0); done = __shfl_sync(SSLAPB_FULL, s_done, 0);
         its = __shfl_sync(SSLAPB_FULL, s_its, 0);
     }
+    // ---- 2..16 bidders: one warp per list position, distributed merge
+    if (nu > 1 && !done) nu = multi_rounds(P, eps, nu, s_list, s_start, s_deg, s_j, s_bidv, its, max_iter, done, rw, li, lst, ldg);
 
     unsigned long long tw1 = sslapb_globaltimer();
-    // ---- single-bidder chain: warp 0 alone, no block barrier
+    // ---- single-bidder chain: warp 0 alone, no block barrier (after multi_rounds warp a holds position a in registers)
     if (warp == 0) {
         if (nu == 1 && !done) nu = chain_rounds(P, eps, li, lst, ldg, its, max_iter, done, rs);
         if (lane == 0) { s_nu = nu; s_done = done; s_its = its; s_rw = rw; s_rs = rs; }
-        if (nu > 0 && lane < nu) P.list[lane] = li;            // only reachable through max_iter
     }
     __syncthreads();
+    if (s_nu > 0 && warp < s_nu && lane == 0 && li >= 0 && (s_nu <= SSLAPB_THREADS / 32)) P.list[warp] = li;   // max_iter exit only
     if (tid == 0) {
         C->nu = s_nu;
         C->its = s_its;
@@ -568,6 +885,11 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
         const float eps_f = *(volatile float *)&C->eps;
         const long long its = *(volatile long long *)&C->its;
         const long long max_iter = *(volatile long long *)&C->max_iter;
+        const int phase_slot = (*(volatile int *)&C->nreductions) & 1;
+        // price bounds for the pruned sweep, taken at the start of the eps-phase: pmin stays a valid lower bound all phase
+        // long (prices never decrease); the spread is only a heuristic for which candidates to gather first
+        const double pmin = sslapb_key2double(*(volatile unsigned long long *)&C->pmin_key[phase_slot]);
+        const float spread = __double2float_ru(sslapb_key2double(*(volatile unsigned long long *)&C->pmax_key) - pmin) + 2.0f * eps_f;
         if (done) break;
 
         if (nu > P.t_small) {
@@ -575,28 +897,38 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
             const double eps = (double)eps_f;
             unsigned long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0, tp5 = 0;
             if (gtid == 0) tp0 = sslapb_globaltimer();
+            int n2nd = 0;
             // (1) bidding: warp per list position (auction_.pyx:339-365) + per-object atomicMax merge (:375-385)
-            for (int a = gwarp; a < nu; a += nwarps) {
-                int v = P.list[a];
-                if (v < -1) {                                  // hole filled by last round's compaction: k-th mover
-                    v = P.mover[-(v + 2)];
-                    if (lane == 0) P.list[a] = v;
-                }
+            auto emit_bid = [&](int a, int j, double bid) {
+                                if (lane == 0) {
+                                    P.bidj[a] = j;
+                                    P.bidv[a] = bid;
+                                    if (j >= 0) {
+                                        const unsigned long long key = sslapb_ord64(bid);
+                                        const unsigned long long old = atomicMax(P.bidkey + j, key);
+                                        if (old == key) *(volatile int *)&C->tie_flag = 1;
+                                    } else {
+                                        *(volatile int *)&C->abort_flag = 2;   // empty row: rejected at CSR build
+                                    }
+                                }
+                            };
+            if (nu > nwarps) {                                 // several rows per warp: software-pipelined sweep
+                sweep_positions(P, P.list, P.mover, nu, gwarp, nwarps, lane, eps, pmin, spread, true, n2nd, emit_bid);
+            } else if (gwarp < nu) {                           // at most one row per warp: nothing to overlap
+                int v = P.list[gwarp];
+                if (v < -1) { v = P.mover[-(v + 2)]; if (lane == 0) P.list[gwarp] = v; }
                 const long long st = __ldg(P.rowptr + v), en = __ldg(P.rowptr + v + 1);
                 int j; double bid;
-                row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);
-                if (lane == 0) {
-                    P.bidj[a] = j;
-                    P.bidv[a] = bid;
-                    if (j >= 0) {
-                        const unsigned long long key = sslapb_ord64(bid);
-                        const unsigned long long old = atomicMax(P.bidkey + j, key);
-                        if (old == key) *(volatile int *)&C->tie_flag = 1;
-                    } else {
-                        *(volatile int *)&C->abort_flag = 2;   // empty row: rejected at CSR build, cannot happen
-                    }
+                if ((((en + 3) >> 2) - (st >> 2)) <= 32) {
+                    const SslapbStreamChunk c = sslapb_stream_chunk(P.cols, P.vals, st, en, lane);
+                    const SslapbBid o = row_bid_pruned(c, P.price, st, en, lane, eps, pmin, spread, n2nd);
+                    j = o.j; bid = o.bid;
+                } else {
+                    row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);
                 }
+                emit_bid(gwarp, j, bid);
             }
+            if (n2nd && lane == 0) atomicAdd((unsigned long long *)&C->prune_second_pass, (unsigned long long)n2nd);
             if (gtid == 0) tp1 = sslapb_globaltimer();
             GB();
             if (gtid == 0) tp2 = sslapb_globaltimer();
@@ -733,7 +1065,20 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
             const bool stop_eps = !stop_opt && (eps_now < teps);   // :280
             if (!stop_opt && !stop_eps) {                      // :283-292 next phase: prices kept, everything else reset
                 for (int i = gtid; i < P.N; i += nthreads) { P.p2o[i] = -1; P.list[i] = i; }
-                for (int j = gtid; j < P.M; j += nthreads) P.rec[j].owner = -1;
+                unsigned long long kmin = ~0ull, kmax = 0ull;  // price range: the next phase's pruning bounds
+                for (int j = gtid; j < P.M; j += nthreads) {
+                    P.rec[j].owner = -1;
+                    const unsigned long long k = sslapb_ord64(P.price[j]);
+                    kmin = k < kmin ? k : kmin;
+                    kmax = k > kmax ? k : kmax;
+                }
+                const unsigned mh = __reduce_min_sync(SSLAPB_FULL, (unsigned)(kmin >> 32));
+                const unsigned ml = __reduce_min_sync(SSLAPB_FULL, (unsigned)(kmin >> 32) == mh ? (unsigned)kmin : 0xffffffffu);
+                const unsigned xh = __reduce_max_sync(SSLAPB_FULL, (unsigned)(kmax >> 32));
+                if (lane == 0) {
+                    atomicMin(&C->pmin_key[phase_slot ^ 1], ((unsigned long long)mh << 32) | ml);
+                    atomicMax(&C->pmax_key, ((unsigned long long)xh << 32) | 0xffffffffull);   // rounded up: heuristic only
+                }
             }
             GB();
             if (gtid == 0) {
@@ -741,6 +1086,7 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
                 else if (stop_eps) { C->done = 2; C->ece_final = 0; }
                 else {
                     C->eps = eps_now * C->theta;               // float32 product (:283)
+                    C->pmin_key[phase_slot] = ~0ull;           // recycled two phases from now
                     C->nreductions += 1;
                     C->nu = P.N;
                 }
@@ -781,7 +1127,7 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
 // Stand-alone bidding sweep (non-cooperative): the grid regime's step (1) for an explicit bidder list.  Used for
 // kernel-level parity (bit-exact (jbest, bid) against the oracle) and for the HBM-roofline measurement of the CSR sweep.
 // ----------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024, 1) sslapb_bid_sweep_kernel(SslapbAuctionParams P, const int *bidders, int nb,
+__global__ void __launch_bounds__(SSLAPB_SWEEP_THREADS, 1) sslapb_bid_sweep_kernel(SslapbAuctionParams P, const int *bidders, int nb,
                                                                   float eps_f, int merge)
 {
     const int lane = threadIdx.x & 31;
@@ -789,17 +1135,20 @@ __global__ void __launch_bounds__(1024, 1) sslapb_bid_sweep_kernel(SslapbAuction
     const int gwarp = blockIdx.x * wpc + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * wpc;
     const double eps = (double)eps_f;
-    for (int a = gwarp; a < nb; a += nwarps) {
-        const int i = bidders ? bidders[a] : a;
-        const long long st = __ldg(P.rowptr + i), en = __ldg(P.rowptr + i + 1);
-        int j; double bid;
-        row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);
-        if (lane == 0) {
-            P.bidj[a] = j;
-            P.bidv[a] = bid;
-            if (merge && j >= 0) atomicMax(P.bidkey + j, sslapb_ord64(bid));
-        }
-    }
+    const bool prune = (merge & 2) == 0;                       // bit 1 of `merge` switches the bound pruning off (A/B measurement)
+    const double pmin = sslapb_key2double(P.ctrl->pmin_key[0]);
+    const float spread = __double2float_ru(sslapb_key2double(P.ctrl->pmax_key) - pmin);
+    int n2nd = 0;
+    merge &= 1;
+    sweep_positions(P, const_cast<int *>(bidders), nullptr, nb, gwarp, nwarps, lane, eps, pmin, spread, prune, n2nd,
+                    [&](int a, int j, double bid) {
+                        if (lane == 0) {
+                            P.bidj[a] = j;
+                            P.bidv[a] = bid;
+                            if (merge && j >= 0) atomicMax(P.bidkey + j, sslapb_ord64(bid));
+                        }
+                    });
+    if (n2nd && lane == 0) atomicAdd((unsigned long long *)&P.ctrl->prune_second_pass, (unsigned long long)n2nd);
 }
 
 // Initial state of a solve (AuctionSolver.__init__, auction_.pyx:220-261).
@@ -832,9 +1181,34 @@ extern "C" cudaError_t sslapb_auction_grid_size(int device, int *grid)
     return cudaSuccess;
 }
 
+// min / max of the current prices into ctrl (stand-alone sweep only; the persistent kernel tracks them itself)
+__global__ void sslapb_price_bounds_kernel(SslapbAuctionParams P, int reset)
+{
+    SslapbCtrl *C = P.ctrl;
+    if (reset) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) { C->pmin_key[0] = ~0ull; C->pmin_key[1] = ~0ull; C->pmax_key = 0ull; C->prune_second_pass = 0; }
+        return;
+    }
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, n = gridDim.x * blockDim.x;
+    unsigned long long kmin = ~0ull, kmax = 0ull;
+    for (int j = gtid; j < P.M; j += n) {
+        const unsigned long long k = sslapb_ord64(P.price[j]);
+        kmin = k < kmin ? k : kmin; kmax = k > kmax ? k : kmax;
+    }
+    atomicMin(&C->pmin_key[0], kmin);
+    atomicMax(&C->pmax_key, kmax);
+}
+
+extern "C" cudaError_t sslapb_launch_price_bounds(const SslapbAuctionParams *P, cudaStream_t stream)
+{
+    sslapb_price_bounds_kernel<<<1, 32, 0, stream>>>(*P, 1);
+    sslapb_price_bounds_kernel<<<64, 256, 0, stream>>>(*P, 0);
+    return cudaGetLastError();
+}
+
 extern "C" cudaError_t sslapb_launch_bid_sweep(const SslapbAuctionParams *P, const int *bidders, int nb, float eps,
                                                int merge, int grid, cudaStream_t stream)
 {
-    sslapb_bid_sweep_kernel<<<grid, 1024, 0, stream>>>(*P, bidders, nb, eps, merge);
+    sslapb_bid_sweep_kernel<<<grid, SSLAPB_SWEEP_THREADS, 0, stream>>>(*P, bidders, nb, eps, merge);
     return cudaGetLastError();
 }

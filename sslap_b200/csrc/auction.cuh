@@ -19,6 +19,10 @@ struct SslapbCtrl {
     int tie_flag;             // some atomicMax saw an equal bid this round -> run the position tie-break pass
     int ece_final;            // meta['eCE'] (:297); -1 until known
     long long rounds_grid, rounds_warp, rounds_solo;   // instrumentation: rounds executed per regime
+    unsigned long long pmin_key[2];                    // order-preserving image of a LOWER bound of every price (slot = phase & 1);
+                                                       // prices never decrease, so a phase-start minimum stays valid all phase
+    unsigned long long pmax_key;                       // running maximum of the prices (atomicMax by every winner): heuristic only
+    long long prune_second_pass;                       // instrumentation: rows that needed the second (exactness) gather pass
     unsigned long long t_begin, t_end;                 // %globaltimer at kernel start / end
     unsigned long long prof2[8];                       // diagnostic builds (-DSSLAPB_PROFILE_SOLO): SM cycles inside single-bidder rounds
     unsigned long long prof[8];                        // ns spent (CTA 0 view): 0 grid bid, 1 grid tie+assign, 2 grid compaction,

@@ -50,4 +50,14 @@ __device__ __forceinline__ double2 sslapb_ldg_stream_d2(const double2 *p)
     return r;
 }
 
+// One 32-byte object record in ONE request (LDG.E.256, sm_100a): a random gather costs the L1TEX pipe per request, not per
+// byte, so a 256-bit load halves the cost of fetching {start, owner, deg, price} compared with 128 + 64 bits.
+struct SslapbRec256 { unsigned long long start, owner_deg, price_bits, pad; };
+__device__ __forceinline__ SslapbRec256 sslapb_ld_rec256(const void *p)
+{
+    SslapbRec256 r;
+    asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.start), "=l"(r.owner_deg), "=l"(r.price_bits), "=l"(r.pad) : "l"(p));
+    return r;
+}
+
 #define SSLAPB_NEG_INF (__longlong_as_double((long long)0xfff0000000000000ull))

@@ -17,7 +17,7 @@ def run(tag, n, d, reps=2, **kw):
         w = time.perf_counter() - t
         m = g["raw"]
         print(f"[{tag}] its={m.its} rounds g/w/s={m.rounds_grid}/{m.rounds_warp}/{m.rounds_solo} solve={m.solve_ms:.2f}ms "
-              f"setup={m.setup_ms:.2f} h2d={m.h2d_ms:.2f} wall={w*1e3:.1f}ms", flush=True)
+              f"setup={m.setup_ms:.2f} h2d={m.h2d_ms:.2f} wall={w*1e3:.1f}ms 2nd_pass_rows={m.prune_second_pass}", flush=True)
         print("    " + "  ".join(f"{k}={v:.2f}ms" for k, v in zip(names, m.prof_ms)))
         per = lambda t, c: (1e3 * t / c) if c else 0.0
         print(f"    per-round us: grid={per(m.prof_ms[0]+m.prof_ms[1]+m.prof_ms[2]+m.prof_ms[7], m.rounds_grid):.2f} "
@@ -28,8 +28,9 @@ if which in ("c2", "both"):
 if which in ("c3", "both"):
     loc, val = run("C3", 100000, 0.001)
     n = 100000
-    for flush in (0, 1):
-        ms = C.c_float(0)
-        rc = L.sslapb_bid_sweep(h.ptr, None, None, n, 0.5, 1, 20, flush, None, None, C.byref(ms))
-        by = 12 * val.size + 36 * n
-        print(f"[C3 full sweep flush={flush}] rc={rc} {ms.value*1e3:.1f} us  {by/ms.value/1e6:.1f} GB/s  frac={by/ms.value/1e6/6544:.3f}", flush=True)
+    for merge in (1, 3):
+        for flush in (0, 1):
+            ms = C.c_float(0)
+            rc = L.sslapb_bid_sweep(h.ptr, None, None, n, 1e-5, merge, 20, flush, None, None, C.byref(ms))
+            by = 12 * val.size + 36 * n
+            print(f"[C3 full sweep prune={'off' if merge & 2 else 'on'} flush={flush}] rc={rc} {ms.value*1e3:.1f} us  {by/ms.value/1e6:.1f} GB/s  frac={by/ms.value/1e6/6544:.3f}", flush=True)
