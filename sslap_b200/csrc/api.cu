@@ -17,6 +17,8 @@
 extern "C" {
 cudaError_t sslapb_launch_coo_ingest(const void *, const void *, int, long long, const double *, long long, int, int, int,
                                      int *, double *, long long *, SslapbBuildFlags *, int, cudaStream_t);
+cudaError_t sslapb_launch_coo_sort(const void *, const void *, int, long long, const double *, long long, int, unsigned *,
+                                   unsigned *, unsigned *, unsigned *, long long *, int *, int *, double *, int, cudaStream_t);
 cudaError_t sslapb_launch_index_max(const void *, const void *, int, long long, long long, long long *, int, cudaStream_t);
 cudaError_t sslapb_launch_dense_count(const double *, int, int, long long *, SslapbBuildFlags *, int, cudaStream_t);
 cudaError_t sslapb_launch_dense_fill(const double *, int, int, int, const long long *, int *, double *,
@@ -68,6 +70,7 @@ struct sslapb_handle {
     long long nnz = 0;
     bool has_vals = false;
     DevBuf stage_idx, stage_val, stage_mat, cols, vals, rowptr, flags;
+    DevBuf sort_keys, sort_idx, sort_hist, sort_rows, sort_cols, sort_val;   // only for unsorted input
     // auction state
     DevBuf price, owner, p2o, list, mover, bidj, bidv, bidkey, winpos, hole_count, chosen, ctrl, bidders, flush;
     // HK state
@@ -116,7 +119,7 @@ extern "C" void sslapb_destroy(sslapb_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *all[] = {&h->stage_idx, &h->stage_val, &h->stage_mat, &h->cols, &h->vals, &h->rowptr, &h->flags, &h->price,
+    DevBuf *all[] = {&h->sort_keys, &h->sort_idx, &h->sort_hist, &h->sort_rows, &h->sort_cols, &h->sort_val, &h->stage_idx, &h->stage_val, &h->stage_mat, &h->cols, &h->vals, &h->rowptr, &h->flags, &h->price,
                      &h->owner, &h->p2o, &h->list, &h->mover, &h->bidj, &h->bidv, &h->bidkey, &h->winpos,
                      &h->hole_count, &h->chosen, &h->ctrl, &h->bidders, &h->flush, &h->pair_u, &h->pair_v, &h->dist,
                      &h->visited, &h->cursor, &h->pred, &h->hkflags};
@@ -208,7 +211,29 @@ static int build_from_coo(sslapb_handle *h, const void *rows, const void *cols, 
     if (nnz == 0) F.empty_rows = 1;
     h->N = n_rows; h->M = n_cols; h->nnz = nnz; h->has_vals = val != nullptr;
     if (F.out_of_range) return fail(h, SSLAPB_E_OUT_OF_RANGE, "loc holds an index outside the matrix");
-    if (F.unsorted) return fail(h, SSLAPB_E_UNSORTED, "loc must be sorted by row (the reference's precondition, auction_.pyx:33-48)");
+    if (F.unsorted) {
+        // The reference silently requires row-sorted input (auction_.pyx:33-48).  Superset behaviour: stable device
+        // radix sort by row (entries of one row keep their input order), then the same ingest pass on the sorted stream.
+        if (nnz >= 0xffffffffll) return fail(h, SSLAPB_E_UNSORTED, "unsorted loc with >= 2^32 entries is not supported");
+        const long long ntiles = (nnz + 4095) / 4096;
+        CK(h->sort_keys.reserve(2 * (size_t)nnz * 4)); CK(h->sort_idx.reserve(2 * (size_t)nnz * 4));
+        CK(h->sort_hist.reserve((size_t)(256 * ntiles + 1024) * 8));
+        CK(h->sort_rows.reserve((size_t)nnz * 4)); CK(h->sort_cols.reserve((size_t)nnz * 4));
+        if (val) CK(h->sort_val.reserve((size_t)nnz * 8));
+        CK(sslapb_launch_coo_sort(d_rows, d_cols, idx_bytes, stride, d_val, nnz, n_rows, h->sort_keys.as<unsigned>(),
+                                  h->sort_keys.as<unsigned>() + nnz, h->sort_idx.as<unsigned>(), h->sort_idx.as<unsigned>() + nnz,
+                                  h->sort_hist.as<long long>(), h->sort_rows.as<int>(), h->sort_cols.as<int>(),
+                                  val ? h->sort_val.as<double>() : nullptr, h->sms, h->stream));
+        CK(cudaMemsetAsync(h->flags.p, 0, sizeof(SslapbBuildFlags), h->stream));
+        CK(cudaMemsetAsync(h->rowptr.p, 0, ((size_t)n_rows + 2) * sizeof(long long), h->stream));
+        CK(sslapb_launch_coo_ingest(h->sort_rows.p, h->sort_cols.p, 4, 1, val ? h->sort_val.as<double>() : nullptr, nnz, n_rows,
+                                    n_cols, negate, h->cols.as<int>(), val ? h->vals.as<double>() : nullptr,
+                                    h->rowptr.as<long long>(), h->flags.as<SslapbBuildFlags>(), h->sms, h->stream));
+        CK(cudaMemcpyAsync(&F, h->flags.p, sizeof F, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(h->ev[2], h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (F.unsorted || F.out_of_range) return fail(h, SSLAPB_E_UNSORTED, "device sort failed (internal error)");
+    }
     return SSLAPB_OK;
 }
 

@@ -162,10 +162,29 @@ def test_infeasible_inputs_raise_like_the_reference(gpu):
         sslap_b200.auction_solve(mat=rng.uniform(1, 9, (6, 4)))
     r = sslap_b200.auction_solve(mat=rng.uniform(1, 9, (4, 6)))
     assert len(set(r["sol"].tolist())) == 4 and r["meta"]["soln_found"] == 1
-    # unsorted loc is the reference's silent precondition; we detect it on the device
-    loc = np.array([[1, 0], [0, 1], [0, 0], [1, 1]], dtype=np.int32)
-    with pytest.raises(ValueError, match="sorted by row"):
-        sslap_b200.auction_solve(loc=loc, val=np.ones(4), size=(2, 2), cardinality_check=False)
+
+
+def test_unsorted_input_is_sorted_on_the_device(gpu, oracle_mod):
+    """The reference needs row-sorted `loc` (auction_.pyx:33-48; unsorted input silently yields garbage there).  The CUDA
+    path detects an unsorted stream and sorts it on the GPU, STABLY: shuffling whole rows around (keeping the order
+    inside each row) must give exactly the result of the sorted stream, ties included."""
+    sslap_b200, nat, h = gpu
+    rng = np.random.default_rng(12)
+    for (n, d, mode) in [(300, 0.05, "int"), (2000, 0.01, "float"), (70000, 0.0005, "float")]:
+        loc, val = make_problem(n, d, mode, seed=13)
+        want = oracle_mod.auction_solve(loc=loc, val=val, problem="min")
+        # shuffled stream: rows dealt into 50 random blocks, original order kept inside every row (what a stable sort undoes)
+        block = rng.integers(0, 50, n)[loc[:, 0]]
+        shuffled = np.lexsort((np.arange(len(val)), block))
+        loc_u, val_u = loc[shuffled], val[shuffled]
+        assert not np.all(np.diff(loc_u[:, 0]) >= 0)
+        for dtype in (np.int32, np.int64):
+            got = sslap_b200.auction_solve(loc=loc_u.astype(dtype), val=val_u, size=(n, n), problem="min",
+                                           cardinality_check=(n <= 2000))
+            assert np.array_equal(got["sol"], want["sol"])
+            assert_meta_equal(got["meta"], want["meta"])
+    hk = sslap_b200.hopcroft_solve(loc=loc_u)
+    assert hk["size"] == n
 
 
 def test_max_iter_returns_partial_assignment(gpu, oracle_mod):
