@@ -9,8 +9,8 @@ A "step" is ONE full auction_solve of BASELINE.json configs[2]: a random 100k x 
   e2e     = same metric through the public Python API (sslap_b200.auction_solve) with HOST (pinned) buffers
   roofline= the full-frontier bidding sweep kernel (the CSR traversal the north star names), CUDA-event timed, L2 flushed
   cpu_baseline = the unmodified reference (oracle/_ref) on ONE host core, one full solve of the same instance
-With N > 1 (torchrun) every rank solves its own instance (seed = rank): the path has no cross-GPU exchange for
-independent problems ("replicas only", weak scaling); times are max over ranks.
+With N > 1 (torchrun) every rank solves its own copy of the instance: the path has no cross-GPU exchange for
+independent problems ("replicas only", weak scaling: equal work per rank); times are max over ranks.
 """
 import argparse
 import ctypes as C
@@ -143,7 +143,7 @@ def main():
     L = nat.load()
     h = nat.Handle(local)
 
-    loc, val = make_problem(N_ROWS, DENSITY, "float", seed=rank)          # one independent instance per rank
+    loc, val = make_problem(N_ROWS, DENSITY, "float", seed=0)             # every rank solves its own copy of the same instance
     nnz = int(val.size)
 
     def barrier():
@@ -228,7 +228,7 @@ def main():
             "metric": "auction_solve_edges_per_s", "value": total_nnz / (ms_step * 1e-3), "unit": "edges/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n": N_ROWS, "nnz_rank0": nnz, "seed": "rank", "parallelism": f"replicas x{world}",
+            "config": {"workload": WORKLOAD, "n": N_ROWS, "nnz_rank0": nnz, "seed": 0, "parallelism": f"replicas x{world}",
                        "l2": "inputs (162 MB COO + 121 MB CSR per step) exceed the 126 MB L2; sweep leg flushes L2 explicitly",
                        "its": its, "objective": obj},
             "solve_s": ms_step * 1e-3,

@@ -109,6 +109,20 @@ int sslapb_hopcroft_coo(sslapb_handle *h, const void *rows, const void *cols, in
 int sslapb_hopcroft_dense(sslapb_handle *h, const double *mat, int32_t n_rows, int32_t n_cols, int mem,
                           int32_t *left_out, int32_t *right_out, int32_t *size_out);
 
+/*
+ * Batch of independent problems (BASELINE.json configs[4]; the reference has no batch call — this replaces a Python loop
+ * of n_problems auction_solve(loc=, val=, cardinality_check=False) calls, auction_solve.py:45-46).
+ *   Problem p owns COO entries [nnz_offsets[p], nnz_offsets[p+1]) of rows/cols/val (indices LOCAL to the problem,
+ *   row-sorted inside the problem) and has n_rows[p] x n_cols[p] shape; nnz_offsets[0] == 0.
+ *   eps_start: per problem (NULL or <= 0 entries: C/2).  sol_out: concatenated, n_rows[p] entries per problem, local
+ *   column ids.  metas: n_problems entries (timings are those of the whole batch).  One warp solves one problem; every
+ *   problem's trajectory (sol, its, meta) is bit-identical to a single-problem call.  No feasibility check is run.
+ */
+int sslapb_auction_batch(sslapb_handle *h, int32_t n_problems, const int64_t *nnz_offsets, const int32_t *n_rows,
+                         const int32_t *n_cols, const void *rows, const void *cols, int idx_bytes, int64_t stride,
+                         const double *val, int maximize, const float *eps_start, int64_t max_iter, int mem,
+                         int32_t *sol_out, sslapb_meta *metas);
+
 /* Prices of the most recent solve on this handle (AuctionSolver.p, auction_.pyx:169,220) — n_cols doubles, host. */
 int sslapb_get_prices(sslapb_handle *h, double *prices_out);
 

@@ -15,7 +15,7 @@ MEM_HOST, MEM_DEVICE_IN, MEM_DEVICE_OUT = 0, 1, 2
 
 EXPORTS = ("sslapb_create", "sslapb_destroy", "sslapb_last_error", "sslapb_set_option", "sslapb_host_alloc",
            "sslapb_host_free", "sslapb_auction_coo", "sslapb_auction_dense", "sslapb_hopcroft_coo",
-           "sslapb_hopcroft_dense", "sslapb_get_prices", "sslapb_bid_sweep")
+           "sslapb_hopcroft_dense", "sslapb_get_prices", "sslapb_bid_sweep", "sslapb_auction_batch")
 
 
 class Meta(C.Structure):
@@ -66,6 +66,8 @@ def load():
     L.sslapb_hopcroft_coo.argtypes = [vp, vp, vp, C.c_int, i64, i64, i32, i32, C.c_int, vp, vp, C.POINTER(i32)]
     L.sslapb_hopcroft_dense.restype = C.c_int
     L.sslapb_hopcroft_dense.argtypes = [vp, vp, i32, i32, C.c_int, vp, vp, C.POINTER(i32)]
+    L.sslapb_auction_batch.restype = C.c_int
+    L.sslapb_auction_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, C.c_int, i64, vp, C.c_int, vp, i64, C.c_int, vp, vp]
     L.sslapb_get_prices.restype = C.c_int
     L.sslapb_get_prices.argtypes = [vp, vp]
     L.sslapb_bid_sweep.restype = C.c_int

@@ -35,6 +35,29 @@ cudaError_t sslapb_hk_launch_augment(const long long *, const int *, int, int, i
                                      int *, SslapbHkFlags *, int, cudaStream_t);
 }
 
+struct SslapbBatchMeta {
+    float start_eps, final_eps, target_eps;
+    int eCE, soln_found, stop_reason;
+    long long its, nreductions, n_assigned;
+};
+struct SslapbBatchParams {
+    int P;
+    const long long *rowoff, *coloff;
+    const long long *rowptr;
+    const int *cols;
+    const double *vals;
+    const float *eps_start;
+    long long max_iter;
+    double *price; int *owner; unsigned long long *bestkey; int *winpos;
+    int *p2o, *list, *mover, *bidj; double *bidv, *chosen;
+    SslapbBatchMeta *meta;
+};
+extern "C" {
+cudaError_t sslapb_launch_batch_globalize(const void *, const void *, int, long long, const long long *, const long long *,
+                                          const long long *, int, int *, int *, int *, int, cudaStream_t);
+cudaError_t sslapb_launch_auction_batch(const SslapbBatchParams *, cudaStream_t);
+}
+
 namespace {
 
 struct DevBuf {
@@ -71,6 +94,7 @@ struct sslapb_handle {
     bool has_vals = false;
     DevBuf stage_idx, stage_val, stage_mat, cols, vals, rowptr, flags;
     DevBuf sort_keys, sort_idx, sort_hist, sort_rows, sort_cols, sort_val;   // only for unsorted input
+    DevBuf b_off, b_rows, b_cols, b_eps, b_meta, b_bad;                      // batched problems
     // auction state
     DevBuf price, owner, p2o, list, mover, bidj, bidv, bidkey, winpos, hole_count, chosen, ctrl, bidders, flush;
     // HK state
@@ -119,7 +143,7 @@ extern "C" void sslapb_destroy(sslapb_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *all[] = {&h->sort_keys, &h->sort_idx, &h->sort_hist, &h->sort_rows, &h->sort_cols, &h->sort_val, &h->stage_idx, &h->stage_val, &h->stage_mat, &h->cols, &h->vals, &h->rowptr, &h->flags, &h->price,
+    DevBuf *all[] = {&h->b_off, &h->b_rows, &h->b_cols, &h->b_eps, &h->b_meta, &h->b_bad, &h->sort_keys, &h->sort_idx, &h->sort_hist, &h->sort_rows, &h->sort_cols, &h->sort_val, &h->stage_idx, &h->stage_val, &h->stage_mat, &h->cols, &h->vals, &h->rowptr, &h->flags, &h->price,
                      &h->owner, &h->p2o, &h->list, &h->mover, &h->bidj, &h->bidv, &h->bidkey, &h->winpos,
                      &h->hole_count, &h->chosen, &h->ctrl, &h->bidders, &h->flush, &h->pair_u, &h->pair_v, &h->dist,
                      &h->visited, &h->cursor, &h->pred, &h->hkflags};
@@ -548,5 +572,128 @@ extern "C" int sslapb_bid_sweep(sslapb_handle *h, const double *prices, const in
     if (bid_out) CK(cudaMemcpyAsync(bid_out, P.bidv, (size_t)nb * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (avg_ms_out) *avg_ms_out = total / (float)iters;
+    return SSLAPB_OK;
+}
+
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Batch of independent problems (BASELINE.json configs[4]) — one warp per problem, see auction.cu
+// ----------------------------------------------------------------------------------------------------------------------
+extern "C" int sslapb_auction_batch(sslapb_handle *h, int32_t n_problems, const int64_t *nnz_offsets, const int32_t *n_rows,
+                                    const int32_t *n_cols, const void *rows, const void *cols, int idx_bytes, int64_t stride,
+                                    const double *val, int maximize, const float *eps_start, int64_t max_iter, int mem,
+                                    int32_t *sol_out, sslapb_meta *metas)
+{
+    if (!h) return SSLAPB_E_BAD_ARG;
+    if (n_problems <= 0 || !nnz_offsets || !n_rows || !n_cols || !rows || !cols || !val || !sol_out)
+        return fail(h, SSLAPB_E_BAD_ARG, "bad batch arguments");
+    CK(cudaSetDevice(h->device));
+    const int P = n_problems;
+    std::vector<long long> off(3 * ((size_t)P + 1));
+    long long *nnzoff = off.data(), *rowoff = nnzoff + P + 1, *coloff = rowoff + P + 1;
+    rowoff[0] = coloff[0] = 0;
+    for (int p = 0; p <= P; ++p) nnzoff[p] = nnz_offsets[p];
+    for (int p = 0; p < P; ++p) {
+        if (n_rows[p] <= 0 || n_cols[p] <= 0 || nnzoff[p + 1] < nnzoff[p]) return fail(h, SSLAPB_E_BAD_ARG, "bad problem shape");
+        if (nnzoff[p + 1] - nnzoff[p] < n_rows[p]) return fail(h, SSLAPB_E_FEWER_THAN_N, "a problem has fewer values than rows");
+        rowoff[p + 1] = rowoff[p] + n_rows[p];
+        coloff[p + 1] = coloff[p] + n_cols[p];
+    }
+    const long long nnz = nnzoff[P] - nnzoff[0], R = rowoff[P], Cn = coloff[P];
+    if (nnzoff[0] != 0 || R >= 0x7fffffffll || Cn >= 0x7fffffffll) return fail(h, SSLAPB_E_BAD_ARG, "batch too large or offsets not starting at 0");
+    const bool interleaved = stride == 2 && (const char *)cols == (const char *)rows + idx_bytes;
+    if (!(interleaved || stride == 1) || (idx_bytes != 4 && idx_bytes != 8)) return fail(h, SSLAPB_E_BAD_ARG, "bad COO layout");
+    // stage the local COO (if on the host) and the offset tables
+    const void *d_rows = rows, *d_cols = cols;
+    const double *d_val = val;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    if (!(mem & SSLAPB_MEM_DEVICE_IN)) {
+        const size_t ib = (size_t)idx_bytes;
+        CK(h->stage_idx.reserve(2 * (size_t)nnz * ib));
+        char *s = h->stage_idx.as<char>();
+        if (interleaved) { CK(cudaMemcpyAsync(s, rows, 2 * (size_t)nnz * ib, cudaMemcpyHostToDevice, h->stream)); d_rows = s; d_cols = s + ib; }
+        else {
+            CK(cudaMemcpyAsync(s, rows, (size_t)nnz * ib, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(s + (size_t)nnz * ib, cols, (size_t)nnz * ib, cudaMemcpyHostToDevice, h->stream));
+            d_rows = s; d_cols = s + (size_t)nnz * ib;
+        }
+        CK(h->stage_val.reserve((size_t)nnz * 8));
+        CK(cudaMemcpyAsync(h->stage_val.p, val, (size_t)nnz * 8, cudaMemcpyHostToDevice, h->stream));
+        d_val = h->stage_val.as<double>();
+    }
+    CK(h->b_off.reserve(off.size() * 8));
+    CK(cudaMemcpyAsync(h->b_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    const long long *d_nnzoff = h->b_off.as<long long>(), *d_rowoff = d_nnzoff + P + 1, *d_coloff = d_rowoff + P + 1;
+    CK(h->b_rows.reserve((size_t)nnz * 4)); CK(h->b_cols.reserve((size_t)nnz * 4)); CK(h->b_bad.reserve(16));
+    CK(cudaMemsetAsync(h->b_bad.p, 0, 16, h->stream));
+    CK(sslapb_launch_batch_globalize(d_rows, d_cols, idx_bytes, stride, d_nnzoff, d_rowoff, d_coloff, P, h->b_rows.as<int>(),
+                                     h->b_cols.as<int>(), h->b_bad.as<int>(), h->sms, h->stream));
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, h->b_bad.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    // one block-diagonal CSR through the ordinary build (sorts on the device if a problem arrives unsorted)
+    SslapbBuildFlags F;
+    memset(&F, 0, sizeof F);
+    int32_t NR = (int32_t)R, NC = (int32_t)Cn;
+    int rc = build_from_coo(h, h->b_rows.p, h->b_cols.p, 4, 1, d_val, nnz, NR, NC, !maximize, SSLAPB_MEM_DEVICE_IN, F);
+    if (rc) return rc;
+    if (bad) return fail(h, SSLAPB_E_OUT_OF_RANGE, "a problem holds an index outside its own shape");
+    if (F.empty_rows) return fail(h, SSLAPB_E_EMPTY_ROW, "a row of some problem has no valid entry");
+    // state
+    CK(h->price.reserve((size_t)Cn * 8)); CK(h->owner.reserve((size_t)Cn * 4));
+    CK(h->bidkey.reserve((size_t)Cn * 8)); CK(h->winpos.reserve((size_t)Cn * 4));
+    CK(h->p2o.reserve((size_t)R * 4)); CK(h->list.reserve((size_t)R * 4)); CK(h->mover.reserve((size_t)R * 4));
+    CK(h->bidj.reserve((size_t)R * 4)); CK(h->bidv.reserve((size_t)R * 8)); CK(h->chosen.reserve((size_t)R * 8));
+    CK(h->b_meta.reserve((size_t)P * sizeof(SslapbBatchMeta)));
+    SslapbBatchParams B;
+    B.P = P; B.rowoff = d_rowoff; B.coloff = d_coloff;
+    B.rowptr = h->rowptr.as<long long>(); B.cols = h->cols.as<int>(); B.vals = h->vals.as<double>();
+    B.eps_start = nullptr;
+    if (eps_start) {
+        CK(h->b_eps.reserve((size_t)P * 4));
+        CK(cudaMemcpyAsync(h->b_eps.p, eps_start, (size_t)P * 4, cudaMemcpyHostToDevice, h->stream));
+        B.eps_start = h->b_eps.as<float>();
+    }
+    B.max_iter = max_iter;
+    B.price = h->price.as<double>(); B.owner = h->owner.as<int>(); B.bestkey = h->bidkey.as<unsigned long long>();
+    B.winpos = h->winpos.as<int>(); B.p2o = h->p2o.as<int>(); B.list = h->list.as<int>(); B.mover = h->mover.as<int>();
+    B.bidj = h->bidj.as<int>(); B.bidv = h->bidv.as<double>(); B.chosen = h->chosen.as<double>();
+    B.meta = h->b_meta.as<SslapbBatchMeta>();
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    CK(sslapb_launch_auction_batch(&B, h->stream));
+    CK(cudaEventRecord(h->ev[4], h->stream));
+    std::vector<SslapbBatchMeta> bm((size_t)P);
+    std::vector<double> chosen((size_t)R);
+    std::vector<int32_t> sol_tmp;
+    int32_t *sol_host = sol_out;
+    if (mem & SSLAPB_MEM_DEVICE_OUT) {
+        CK(cudaMemcpyAsync(sol_out, B.p2o, (size_t)R * 4, cudaMemcpyDeviceToDevice, h->stream));
+        sol_tmp.resize((size_t)R); sol_host = sol_tmp.data();
+    }
+    CK(cudaMemcpyAsync(sol_host, B.p2o, (size_t)R * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(chosen.data(), B.chosen, (size_t)R * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(bm.data(), B.meta, (size_t)P * sizeof(SslapbBatchMeta), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float setup_ms = 0, solve_ms = 0, h2d_ms = 0;
+    cudaEventElapsedTime(&setup_ms, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&solve_ms, h->ev[3], h->ev[4]);
+    cudaEventElapsedTime(&h2d_ms, h->ev[0], h->ev[1]);
+    if (metas) {
+        for (int p = 0; p < P; ++p) {
+            sslapb_meta &m = metas[p];
+            memset(&m, 0, sizeof m);
+            double obj = 0.0;
+            for (long long i = rowoff[p]; i < rowoff[p + 1]; ++i) {
+                if (sol_host[i] == -1) continue;
+                if (maximize) obj += chosen[(size_t)i]; else obj -= chosen[(size_t)i];
+            }
+            m.start_eps = bm[p].start_eps; m.final_eps = bm[p].final_eps; m.target_eps = bm[p].target_eps;
+            m.eCE = bm[p].eCE; m.soln_found = bm[p].soln_found; m.its = bm[p].its; m.nreductions = bm[p].nreductions;
+            m.n_assigned = bm[p].n_assigned; m.obj64 = obj; m.obj = (float)obj;
+            m.setup_ms = setup_ms; m.solve_ms = solve_ms; m.h2d_ms = h2d_ms;      // times of the WHOLE batch
+            m.cardinality = -1; m.n_rows = n_rows[p]; m.n_cols = n_cols[p]; m.nnz = nnzoff[p + 1] - nnzoff[p];
+            m.stop_reason = bm[p].stop_reason;
+        }
+    }
+    h->has_vals = false;                                       // the resident CSR is block-diagonal: not a single problem
     return SSLAPB_OK;
 }

@@ -1212,3 +1212,240 @@ extern "C" cudaError_t sslapb_launch_bid_sweep(const SslapbAuctionParams *P, con
     sslapb_bid_sweep_kernel<<<grid, SSLAPB_SWEEP_THREADS, 0, stream>>>(*P, bidders, nb, eps, merge);
     return cudaGetLastError();
 }
+
+// ======================================================================================================================
+// Batched small problems (BASELINE.json configs[4]: thousands of independent 512 x 512 problems): ONE WARP PER PROBLEM.
+//
+// Every auction is a chain of dependent rounds, so a single small problem cannot use more than a sliver of the GPU;
+// throughput comes from running thousands of those chains at once (148 SMs x 32 resident warps = 4736 problems in
+// flight).  Each warp executes the reference's round literally on its own problem — bidding over the unassigned list
+// (row sweep by the 32 lanes, auction_.pyx:339-365), merge by atomicMax on the order-preserving bid + list-position
+// tie-break (:375-385), winner-driven assignment (:394-427), push_all_left in list order (:137-162), eps-scaling and the
+// eps-CS test (:268-309, :443-485) — so `sol`, `its` and every meta key are bit-identical to a reference call per problem.
+// The problems are stored block-diagonally in ONE CSR (global row/column ids), built by the ordinary ingest pass.
+// ======================================================================================================================
+struct SslapbBatchMeta {
+    float start_eps, final_eps, target_eps;
+    int eCE, soln_found, stop_reason;
+    long long its, nreductions, n_assigned;
+};
+
+struct SslapbBatchParams {
+    int P;
+    const long long *rowoff, *coloff;     // P+1 prefix sums of the problems' row / column counts
+    const long long *rowptr;              // global CSR
+    const int *cols;                      // global column ids
+    const double *vals;                   // sign-folded
+    const float *eps_start;               // per problem, <= 0 => C/2 (nullable)
+    long long max_iter;
+    double *price; int *owner; unsigned long long *bestkey; int *winpos;      // per global column
+    int *p2o, *list, *mover, *bidj; double *bidv, *chosen;                    // per global row
+    SslapbBatchMeta *meta;
+};
+
+__device__ __forceinline__ bool batch_ece(const SslapbBatchParams &B, long long r0, int N, int lane, float teps)
+{
+    const double eps_t = (double)teps;
+    bool viol = false;
+    for (int i = 0; i < N; ++i) {
+        const long long g = r0 + i;
+        const int j = B.p2o[g];
+        double vmax, choice, csum;
+        row_ece(B.cols, B.vals, B.price, __ldg(B.rowptr + g), __ldg(B.rowptr + g + 1), lane, j, vmax, choice, csum);
+        if (((choice - B.price[j]) + 1e-7) < vmax - eps_t) viol = true;
+    }
+    return !__any_sync(SSLAPB_FULL, viol);
+}
+
+__global__ void __launch_bounds__(128) sslapb_auction_batch_kernel(SslapbBatchParams B)
+{
+    const int lane = threadIdx.x & 31;
+    const int p = __shfl_sync(SSLAPB_FULL, (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), 0);
+    if (p >= B.P) return;
+    const long long r0 = B.rowoff[p], c0 = B.coloff[p];
+    const int N = (int)(B.rowoff[p + 1] - r0), M = (int)(B.coloff[p + 1] - c0);
+    // ---- AuctionSolver.__init__ (auction_.pyx:220-261)
+    for (int j = lane; j < M; j += 32) { B.price[c0 + j] = 0.0; B.owner[c0 + j] = -1; B.bestkey[c0 + j] = 0ull; B.winpos[c0 + j] = 0x7fffffff; }
+    for (int i = lane; i < N; i += 32) { B.p2o[r0 + i] = -1; B.list[r0 + i] = (int)(r0 + i); }
+    double cmax = 0.0;                                         // max_val (:123-134)
+    for (long long e = __ldg(B.rowptr + r0) + lane; e < __ldg(B.rowptr + r0 + N); e += 32) cmax = fmax(cmax, fabs(B.vals[e]));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) cmax = fmax(cmax, __shfl_xor_sync(SSLAPB_FULL, cmax, off));
+    float eps = (float)((double)((float)cmax) / 2.0);          // :242-246
+    const float target = (float)(1.0 / (double)N), theta = 0.15f;
+    if (B.eps_start && B.eps_start[p] > 0) eps = B.eps_start[p];
+    const float start_eps = eps;
+    __syncwarp();
+
+    int nu = N, stop = 0, nred = 0, last_opt = -1;
+    long long its = 0;
+    int dummy2nd = 0;
+    for (;;) {
+        const double epsd = (double)eps;
+        // ---- bidding (:339-365): the unassigned list in order, one row sweep at a time
+        for (int n = 0; n < nu; ++n) {
+            const int i = B.list[r0 + n];
+            const long long st = __ldg(B.rowptr + i), en = __ldg(B.rowptr + i + 1);
+            int j; double bid;
+            if ((((en + 3) >> 2) - (st >> 2)) <= 32) {
+                const SslapbStreamChunk c = sslapb_stream_chunk(B.cols, B.vals, st, en, lane);
+                const SslapbBid o = row_bid_pruned(c, B.price, st, en, lane, epsd, 0.0, __int_as_float(0x7f800000), dummy2nd);
+                j = o.j; bid = o.bid;
+            } else {
+                row_bid<32>(B.cols, B.vals, B.price, st, en, lane, epsd, j, bid);
+            }
+            if (lane == 0) { B.bidj[r0 + n] = j; B.bidv[r0 + n] = bid; }
+        }
+        __syncwarp();
+        // ---- merge (:375-385): per-object maximum of the order-preserving bid, earliest list position on equal bids
+        bool tie = false;
+        for (int base = 0; base < nu; base += 32) {
+            const int n = base + lane;
+            if (n < nu) {
+                const int j = B.bidj[r0 + n];
+                if (j >= 0) {
+                    const unsigned long long key = sslapb_ord64(B.bidv[r0 + n]);
+                    if (atomicMax(B.bestkey + j, key) == key) tie = true;
+                }
+            }
+        }
+        tie = __any_sync(SSLAPB_FULL, tie);
+        if (tie) {
+            for (int base = 0; base < nu; base += 32) {
+                const int n = base + lane;
+                if (n < nu) {
+                    const int j = B.bidj[r0 + n];
+                    if (j >= 0 && __ldcg(B.bestkey + j) == sslapb_ord64(B.bidv[r0 + n])) atomicMin(B.winpos + j, n);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- assignment (:394-427)
+        int holes = 0;
+        for (int base = 0; base < nu; base += 32) {
+            const int n = base + lane;
+            bool hole = false;
+            if (n < nu) {
+                const int j = B.bidj[r0 + n];
+                const double bid = B.bidv[r0 + n];
+                const bool win = j >= 0 && (__ldcg(B.bestkey + j) == sslapb_ord64(bid)) && (!tie || __ldcg(B.winpos + j) == n);
+                if (win) {
+                    const int i = B.list[r0 + n];
+                    const int prev = B.owner[j];
+                    B.price[j] = bid;
+                    B.owner[j] = i;
+                    B.p2o[i] = j;
+                    if (prev >= 0) B.p2o[prev] = -1;
+                    B.list[r0 + n] = prev;
+                    hole = prev < 0;
+                }
+            }
+            holes += __popc(__ballot_sync(SSLAPB_FULL, hole));
+        }
+        // reset best-bid slots of every object that received a bid (auction_.pyx:421-422)
+        for (int base = 0; base < nu; base += 32) {
+            const int n = base + lane;
+            if (n < nu) {
+                const int j = B.bidj[r0 + n];
+                if (j >= 0) { B.bestkey[j] = 0ull; B.winpos[j] = 0x7fffffff; }
+            }
+        }
+        __syncwarp();
+        // ---- push_all_left (:137-162): k-th hole left of the new count <- k-th live entry right of it
+        const int new_nu = nu - holes;
+        if (holes && new_nu > 0) {
+            int k = 0;
+            for (int base = new_nu & ~31; base < nu; base += 32) {
+                const int n = base + lane;
+                const bool live = n >= new_nu && n < nu && B.list[r0 + n] >= 0;
+                const unsigned bal = __ballot_sync(SSLAPB_FULL, live);
+                if (live) B.mover[r0 + k + __popc(bal & ((1u << lane) - 1u))] = B.list[r0 + n];
+                k += __popc(bal);
+            }
+            __syncwarp();
+            int q = 0;
+            for (int base = 0; base < new_nu && q < k; base += 32) {
+                const int n = base + lane;
+                const bool hole = n < new_nu && B.list[r0 + n] < 0;
+                const unsigned bal = __ballot_sync(SSLAPB_FULL, hole);
+                if (hole) B.list[r0 + n] = B.mover[r0 + q + __popc(bal & ((1u << lane) - 1u))];
+                q += __popc(bal);
+            }
+            __syncwarp();
+        }
+        nu = new_nu;
+        ++its;
+        last_opt = -1;
+        // ---- terminate() / eps-scaling (:275-292)
+        if (its >= B.max_iter) { stop = 3; break; }
+        if (nu == 0) {
+            last_opt = batch_ece(B, r0, N, lane, target) ? 1 : 0;
+            if (last_opt) { stop = 1; break; }
+            if (eps < target) { stop = 2; break; }
+            eps = eps * theta;
+            for (int j = lane; j < M; j += 32) B.owner[c0 + j] = -1;
+            for (int i = lane; i < N; i += 32) { B.p2o[r0 + i] = -1; B.list[r0 + i] = (int)(r0 + i); }
+            __syncwarp();
+            nu = N;
+            ++nred;
+        }
+    }
+    if (last_opt < 0) last_opt = (nu == 0 && batch_ece(B, r0, N, lane, target)) ? 1 : 0;
+    // ---- get_obj (:489-523): per-person chosen values (summed on the host in row order) and local column ids
+    for (int i = 0; i < N; ++i) {
+        const long long g = r0 + i;
+        const int j = B.p2o[g];
+        double csum = 0.0;
+        if (j >= 0) {
+            double vmax, choice;
+            row_ece(B.cols, B.vals, B.price, __ldg(B.rowptr + g), __ldg(B.rowptr + g + 1), lane, j, vmax, choice, csum);
+        }
+        if (lane == 0) { B.chosen[g] = csum; B.p2o[g] = j >= 0 ? (int)(j - c0) : -1; }
+    }
+    if (lane == 0) {
+        SslapbBatchMeta m;
+        m.start_eps = start_eps; m.final_eps = eps; m.target_eps = target;
+        m.eCE = last_opt; m.soln_found = (nu == 0 && last_opt) ? 1 : 0; m.stop_reason = stop;
+        m.its = its; m.nreductions = nred; m.n_assigned = N - nu;
+        B.meta[p] = m;
+    }
+}
+
+// local (row, col) -> global block-diagonal ids; one CTA per problem
+template <typename IT>
+__global__ void __launch_bounds__(256) sslapb_batch_globalize_kernel(const IT *__restrict__ rows, const IT *__restrict__ cols,
+                                                                     long long stride, const long long *__restrict__ nnzoff,
+                                                                     const long long *__restrict__ rowoff,
+                                                                     const long long *__restrict__ coloff, int P,
+                                                                     int *__restrict__ rows_g, int *__restrict__ cols_g, int *bad)
+{
+    for (int p = blockIdx.x; p < P; p += gridDim.x) {
+        const long long r0 = rowoff[p], c0 = coloff[p];
+        const long long N = rowoff[p + 1] - r0, M = coloff[p + 1] - c0;
+        for (long long k = nnzoff[p] + threadIdx.x; k < nnzoff[p + 1]; k += blockDim.x) {
+            const long long r = (long long)rows[k * stride], c = (long long)cols[k * stride];
+            if (r < 0 || r >= N || c < 0 || c >= M) { *bad = 1; rows_g[k] = (int)r0; cols_g[k] = (int)c0; }
+            else { rows_g[k] = (int)(r0 + r); cols_g[k] = (int)(c0 + c); }
+        }
+    }
+}
+
+extern "C" cudaError_t sslapb_launch_batch_globalize(const void *rows, const void *cols, int idx_bytes, long long stride,
+                                                     const long long *nnzoff, const long long *rowoff, const long long *coloff,
+                                                     int P, int *rows_g, int *cols_g, int *bad, int sms, cudaStream_t stream)
+{
+    const int grid = P < sms * 8 ? P : sms * 8;
+    if (idx_bytes == 4)
+        sslapb_batch_globalize_kernel<int><<<grid, 256, 0, stream>>>((const int *)rows, (const int *)cols, stride, nnzoff, rowoff, coloff, P, rows_g, cols_g, bad);
+    else
+        sslapb_batch_globalize_kernel<long long><<<grid, 256, 0, stream>>>((const long long *)rows, (const long long *)cols, stride, nnzoff, rowoff, coloff, P, rows_g, cols_g, bad);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t sslapb_launch_auction_batch(const SslapbBatchParams *B, cudaStream_t stream)
+{
+    const int warps_per_cta = 4;
+    const int grid = (B->P + warps_per_cta - 1) / warps_per_cta;
+    sslapb_auction_batch_kernel<<<grid, 32 * warps_per_cta, 0, stream>>>(*B);
+    return cudaGetLastError();
+}

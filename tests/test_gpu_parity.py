@@ -222,3 +222,35 @@ def test_c3_full_size_properties_and_oracle(gpu, oracle_mod):
     assert np.array_equal(sol, o["sol"])
     assert_meta_equal(r["meta"], o["meta"])
     assert abs(obj - 162903.850803) < 1e-4                                  # SURVEY.md §6.2 (reference run)
+
+
+def test_batch_matches_single_problem_calls(gpu, oracle_mod):
+    """BASELINE.json configs[4] shape (512 x 512 at 5 %): every problem of a batch must come back bit-identical to the
+    oracle's (= the reference's) answer for that problem, ties and max_iter included."""
+    sslap_b200, nat, h = gpu
+    probs, want = [], []
+    for k in range(40):
+        n = 512 if k < 8 else int(20 + 13 * k)
+        mode = "int" if k % 3 == 0 else "float"
+        loc, val = make_problem(n, 0.05 if n == 512 else 0.2, mode, seed=100 + k)
+        probs.append((loc, val, (n, n)))
+        want.append(oracle_mod.auction_solve(loc=loc, val=val, problem="max"))
+    got = sslap_b200.auction_solve_batch(probs, problem="max")
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert np.array_equal(g["sol"], w["sol"])
+        assert_meta_equal(g["meta"], w["meta"])
+    # golden: the reference's own result for one 512 x 512 problem, run as a batch of copies
+    gold = load_golden("c5_one")
+    res = sslap_b200.auction_solve_batch([(gold["loc"], gold["val"], (512, 512))] * 5, problem=gold["problem"])
+    for r in res:
+        assert np.array_equal(r["sol"], gold["sol"])
+        assert_meta_equal(r["meta"], gold["meta"])
+    # max_iter truncation and eps_start / fast
+    loc, val = make_problem(200, 0.1, "int", seed=5)
+    for kw in (dict(max_iter=37), dict(eps_start=1.0), dict(fast=True)):
+        r = sslap_b200.auction_solve_batch([(loc, val, (200, 200))] * 3, **kw)[1]
+        o = oracle_mod.auction_solve(loc=loc, val=val, **{k: v for k, v in kw.items() if k != "fast"},
+                                     **({"eps_start": float(np.float32(1.0 / 200))} if kw.get("fast") else {}))
+        assert np.array_equal(r["sol"], o["sol"])
+        assert_meta_equal(r["meta"], o["meta"])
