@@ -17,20 +17,35 @@
 #define HK_INF 0x7fffffff
 
 
-// Cheap maximal-matching initialisation: every left vertex grabs its first free neighbour.
+// Cheap maximal-matching initialisation: every left vertex grabs its first free neighbour (warp per vertex: the lanes scan
+// the adjacency list together, the free neighbours are tried in adjacency order).
 __global__ void __launch_bounds__(256) sslapb_hk_greedy_kernel(const long long *__restrict__ rowptr,
                                                                const int *__restrict__ cols, int N, int *pair_u,
                                                                int *pair_v, SslapbHkFlags *F)
 {
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     int got = 0;
-    for (int u = gtid; u < N; u += nth) {
-        for (long long e = rowptr[u]; e < rowptr[u + 1]; ++e) {
-            const int v = cols[e];
-            if (pair_v[v] == -1 && atomicCAS(pair_v + v, -1, u) == -1) { pair_u[u] = v; ++got; break; }
+    for (int u = gwarp; u < N; u += nwarps) {
+        const long long st = rowptr[u], en = rowptr[u + 1];
+        bool done = false;
+        for (long long base = st; base < en && !done; base += 32) {
+            const long long e = base + lane;
+            int v = -1;
+            bool fr = false;
+            if (e < en) { v = cols[e]; fr = *(volatile int *)(pair_v + v) == -1; }
+            unsigned cand = __ballot_sync(SSLAPB_FULL, fr);
+            while (cand && !done) {
+                const int l = __ffs(cand) - 1;
+                cand &= cand - 1;
+                int ok = 0;
+                if (lane == l) ok = atomicCAS(pair_v + v, -1, u) == -1;
+                ok = __shfl_sync(SSLAPB_FULL, ok, l);
+                if (ok) { if (lane == l) pair_u[u] = v; done = true; ++got; }
+            }
         }
     }
-    if (got) atomicAdd(&F->matched, got);
+    if (got && lane == 0) atomicAdd(&F->matched, got);
 }
 
 __global__ void __launch_bounds__(256) sslapb_hk_phase_init_kernel(int N, int M, const int *__restrict__ pair_u,
@@ -64,67 +79,90 @@ __global__ void __launch_bounds__(256) sslapb_hk_bfs_level_kernel(const long lon
     if (grew) F->grew = 1;
 }
 
-// Augmentation: one thread per free left vertex walks the level graph depth-first.  Left vertices are reached only
-// through their (claimed) partner, so cursor[]/pred[] entries are private to the walking thread.
+// Augmentation: one WARP per free left vertex walks the level graph depth-first; the 32 lanes scan the adjacency list of
+// the current vertex together (coalesced), the eligible neighbours are claimed one at a time in adjacency order (a claim
+// that is not used would block other searches for nothing).  Left vertices are reached only through their (claimed)
+// partner, so cursor[]/pred[] entries are private to the walking warp.
 __global__ void __launch_bounds__(128) sslapb_hk_augment_kernel(const long long *__restrict__ rowptr,
                                                                 const int *__restrict__ cols, int N, int dist_nil,
                                                                 int *pair_u, int *pair_v, int *dist, int *visited,
                                                                 long long *cursor, int *pred, SslapbHkFlags *F)
 {
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     int wins = 0;
-    for (int root = gtid; root < N; root += nth) {
-        if (dist[root] != 0) continue;                         // free left vertices are exactly the level-0 ones
+    for (int root = gwarp; root < N; root += nwarps) {
+        if (*(volatile int *)(dist + root) != 0) continue;     // free left vertices are exactly the level-0 ones
         int cur = root;
-        cursor[cur] = rowptr[cur];
-        pred[cur] = -1;
+        if (lane == 0) { cursor[cur] = rowptr[cur]; pred[cur] = -1; }
+        __syncwarp();
         for (;;) {
             const long long en = rowptr[cur + 1];
-            const int want = dist[cur] + 1;
-            long long e = cursor[cur];
-            int next = -2;                                     // -2 none, -1 free right vertex, >= 0 left vertex to descend to
-            int via = -1;
-            for (; e < en; ++e) {
-                const int v = cols[e];
-                const int pu = *(volatile int *)(pair_v + v);
-                const int dpu = (pu == -1) ? dist_nil : *(volatile int *)(dist + pu);
-                if (dpu != want) continue;                     // feasibility_.pyx:186
-                if (atomicExch(visited + v, 1) != 0) continue; // someone else owns v in this phase
-                next = pu; via = v; ++e;
-                break;
+            const int want = *(volatile int *)(dist + cur) + 1;
+            long long base = *(volatile long long *)(cursor + cur);
+            int next = -2, via = -1;                           // -2 none, -1 free right vertex, >= 0 left vertex to descend to
+            long long resume = en;
+            while (base < en && next == -2) {
+                const long long e = base + lane;
+                int v = -1, pu = -1;
+                bool ok = false;
+                if (e < en) {
+                    v = cols[e];
+                    pu = *(volatile int *)(pair_v + v);
+                    const int dpu = (pu == -1) ? dist_nil : *(volatile int *)(dist + pu);
+                    ok = (dpu == want) && (*(volatile int *)(visited + v) == 0);   // feasibility_.pyx:186
+                }
+                unsigned cand = __ballot_sync(SSLAPB_FULL, ok);
+                while (cand && next == -2) {                   // claim in adjacency order, one at a time
+                    const int l = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    int got = 0;
+                    if (lane == l) got = (atomicExch(visited + v, 1) == 0);
+                    got = __shfl_sync(SSLAPB_FULL, got, l);
+                    if (got) {
+                        next = __shfl_sync(SSLAPB_FULL, pu, l);
+                        via = __shfl_sync(SSLAPB_FULL, v, l);
+                        resume = base + l + 1;
+                    }
+                }
+                base += 32;
             }
-            cursor[cur] = e;
+            if (lane == 0) cursor[cur] = resume;
             if (next == -2) {                                  // dead end (:194)
-                dist[cur] = HK_INF;
+                if (lane == 0) dist[cur] = HK_INF;
                 if (cur == root) break;
                 cur = pred[cur];
+                __syncwarp();
                 continue;
             }
             if (next == -1) {                                  // free right vertex: flip the path (:189-190)
-                int u = cur, v = via;
-                for (;;) {
-                    const int old_v = pair_u[u];
-                    pair_u[u] = v;
-                    pair_v[v] = u;
-                    if (u == root) break;
-                    v = old_v;
-                    u = pred[u];
+                if (lane == 0) {
+                    int u = cur, v = via;
+                    for (;;) {
+                        const int old_v = pair_u[u];
+                        pair_u[u] = v;
+                        pair_v[v] = u;
+                        if (u == root) break;
+                        v = old_v;
+                        u = pred[u];
+                    }
                 }
+                __syncwarp();
                 ++wins;
                 break;
             }
-            pred[next] = cur;
-            cursor[next] = rowptr[next];
+            if (lane == 0) { pred[next] = cur; cursor[next] = rowptr[next]; }
+            __syncwarp();
             cur = next;
         }
     }
-    if (wins) atomicAdd(&F->augmented, wins);
+    if (wins && lane == 0) atomicAdd(&F->augmented, wins);
 }
 
 extern "C" cudaError_t sslapb_hk_launch_greedy(const long long *rowptr, const int *cols, int N, int *pair_u, int *pair_v,
                                                SslapbHkFlags *F, int sms, cudaStream_t s)
 {
-    sslapb_hk_greedy_kernel<<<sms * 4, 256, 0, s>>>(rowptr, cols, N, pair_u, pair_v, F);
+    sslapb_hk_greedy_kernel<<<sms * 8, 256, 0, s>>>(rowptr, cols, N, pair_u, pair_v, F);
     return cudaGetLastError();
 }
 extern "C" cudaError_t sslapb_hk_launch_phase_init(int N, int M, const int *pair_u, int *dist, int *visited,
@@ -144,7 +182,7 @@ extern "C" cudaError_t sslapb_hk_launch_augment(const long long *rowptr, const i
                                                 int *pair_v, int *dist, int *visited, long long *cursor, int *pred,
                                                 SslapbHkFlags *F, int sms, cudaStream_t s)
 {
-    sslapb_hk_augment_kernel<<<sms * 4, 128, 0, s>>>(rowptr, cols, N, dist_nil, pair_u, pair_v, dist, visited, cursor,
+    sslapb_hk_augment_kernel<<<sms * 8, 128, 0, s>>>(rowptr, cols, N, dist_nil, pair_u, pair_v, dist, visited, cursor,
                                                      pred, F);
     return cudaGetLastError();
 }
