@@ -5,7 +5,7 @@ the CUDA library is loaded on first use and there is no CPU fallback.
 """
 from .auction_solve import auction_solve
 from .check_feasible import hopcroft_solve
-from .batch import auction_solve_batch
+from .batch import auction_solve_batch, pack_problems
 
 __version__ = "0.1.0"
-__all__ = ["auction_solve", "hopcroft_solve", "auction_solve_batch"]
+__all__ = ["auction_solve", "hopcroft_solve", "auction_solve_batch", "pack_problems"]

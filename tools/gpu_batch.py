@@ -10,6 +10,12 @@ t = time.perf_counter()
 base = [make_problem(512, 0.05, "float", seed=s) for s in range(64)]
 probs = [(base[k % 64][0], base[k % 64][1], (512, 512)) for k in range(P)]
 print(f"generated {P} problems ({time.perf_counter()-t:.1f}s), nnz/problem ~{len(base[0][1])}", flush=True)
+t = time.perf_counter(); packed = sslap_b200.pack_problems(probs); print(f"pack_problems {time.perf_counter()-t:.3f}s")
+for rep in range(2):
+    t = time.perf_counter()
+    r = sslap_b200.auction_solve_batch(packed, packed_result=True)
+    dt = time.perf_counter() - t
+    print(f"packed rep {rep}: wall {dt*1e3:.1f} ms  kernel {r['metas'][0].solve_ms:.1f} ms  h2d {r['metas'][0].h2d_ms:.1f} ms  {P/dt:.0f} problems/s", flush=True)
 for rep in range(3):
     t = time.perf_counter()
     res = sslap_b200.auction_solve_batch(probs)
