@@ -30,7 +30,6 @@ __device__ __forceinline__ long long sslapb_clk_after(int dep)
 #else
 #define SSLAPB_PROBE(K_, DEP_) do { } while (0)
 #endif
-#define SSLAPB_SWEEP_THREADS 768 // stand-alone sweep: 24 warps per SM, 85 registers each (two rows in flight per warp)
 #define SSLAPB_THREADS 512       // persistent kernel: one CTA of 16 warps per SM (128 registers per thread)
 
 // ----------------------------------------------------------------------------------------------------------------------
@@ -336,57 +335,6 @@ __device__ __noinline__ SslapbBid row_bid_rec(const int *__restrict__ cols, cons
                                               double eps, long long *acc = nullptr)
 {
     return row_bid_core<W, true>(cols, vals, nullptr, rec, start, end, t, eps, acc);
-}
-
-// Bidding step of the grid regime over list positions a = first, first+stride, ... < nb, software-pipelined inside every
-// warp: while row m is being processed (price gathers + top-2), the entries of row m+1 are already in flight, the row
-// offsets of row m+2 are being fetched and the person of position m+3 is being read.  Without this the sweep is a
-// chain of four dependent round trips per row per warp and runs at ~30 % of the HBM roofline regardless of the
-// number of gathers.  `persons` = NULL means position == person (full frontier).
-template <typename Emit>
-__device__ __forceinline__ void sweep_positions(const SslapbAuctionParams &P, int *persons, const int *mover, int nb,
-                                                int first, int stride, int lane, double eps, double pmin, float spread,
-                                                bool prune, int &second_pass, Emit emit)
-{
-    if (first >= nb) return;
-    // pipeline registers: person ids two and three positions ahead, row offsets one and two ahead, entries one ahead
-    auto person_at = [&](int a) -> int { return (a < nb) ? (persons ? persons[a] : a) : -1; };
-    auto decode = [&](int a, int v) -> int {                  // rank-encoded hole left by the previous compaction
-        if (v < -1) { v = mover[-(v + 2)]; if (lane == 0) persons[a] = v; }
-        return v;
-    };
-    int a0 = first;
-    int v0 = decode(a0, person_at(a0));
-    int v1 = person_at(a0 + stride);
-    int v2 = person_at(a0 + 2 * stride);
-    long long st0 = __ldg(P.rowptr + v0), en0 = __ldg(P.rowptr + v0 + 1);
-    v1 = (a0 + stride < nb) ? decode(a0 + stride, v1) : -1;
-    long long st1 = 0, en1 = 0;
-    if (v1 >= 0) { st1 = __ldg(P.rowptr + v1); en1 = __ldg(P.rowptr + v1 + 1); }
-    SslapbStreamChunk c0 = sslapb_stream_chunk(P.cols, P.vals, st0, en0, lane);
-    for (;;) {
-        const int a1 = a0 + stride, a2 = a0 + 2 * stride, a3 = a0 + 3 * stride;
-        // stage A: person of position m+3
-        const int v3 = person_at(a3);
-        // stage B: row offsets of position m+2
-        long long st2 = 0, en2 = 0;
-        if (a2 < nb) { v2 = decode(a2, v2); st2 = __ldg(P.rowptr + v2); en2 = __ldg(P.rowptr + v2 + 1); }
-        // stage C: entries of position m+1
-        SslapbStreamChunk c1;
-        c1.cj = make_int4(0, 0, 0, 0); c1.va = make_double2(0.0, 0.0); c1.vb = c1.va;
-        if (a1 < nb) c1 = sslapb_stream_chunk(P.cols, P.vals, st1, en1, lane);
-        // stage D: process position m
-        int j; double bid;
-        if (prune && (((en0 + 3) >> 2) - (st0 >> 2)) <= 32) {
-            const SslapbBid o = row_bid_pruned(c0, P.price, st0, en0, lane, eps, pmin, spread, second_pass);
-            j = o.j; bid = o.bid;
-        } else {
-            row_bid<32>(P.cols, P.vals, P.price, st0, en0, lane, eps, j, bid);
-        }
-        emit(a0, j, bid);
-        if (a1 >= nb) break;
-        a0 = a1; st0 = st1; en0 = en1; c0 = c1; st1 = st2; en1 = en2; v2 = v3;
-    }
 }
 
 // eCE / objective sweep of one row by a full warp (auction_.pyx:460-483 and :504-521).
@@ -912,11 +860,10 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
                                     }
                                 }
                             };
-            if (nu > nwarps) {                                 // several rows per warp: software-pipelined sweep
-                sweep_positions(P, P.list, P.mover, nu, gwarp, nwarps, lane, eps, pmin, spread, true, n2nd, emit_bid);
-            } else if (gwarp < nu) {                           // at most one row per warp: nothing to overlap
-                int v = P.list[gwarp];
-                if (v < -1) { v = P.mover[-(v + 2)]; if (lane == 0) P.list[gwarp] = v; }
+            // (a software pipeline across rows was measured to buy nothing: the sweep is instruction-issue bound)
+            for (int a = gwarp; a < nu; a += nwarps) {
+                int v = P.list[a];
+                if (v < -1) { v = P.mover[-(v + 2)]; if (lane == 0) P.list[a] = v; }   // hole filled by the last compaction
                 const long long st = __ldg(P.rowptr + v), en = __ldg(P.rowptr + v + 1);
                 int j; double bid;
                 if ((((en + 3) >> 2) - (st >> 2)) <= 32) {
@@ -926,7 +873,7 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
                 } else {
                     row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);
                 }
-                emit_bid(gwarp, j, bid);
+                emit_bid(a, j, bid);
             }
             if (n2nd && lane == 0) atomicAdd((unsigned long long *)&C->prune_second_pass, (unsigned long long)n2nd);
             if (gtid == 0) tp1 = sslapb_globaltimer();
@@ -1127,7 +1074,7 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
 // Stand-alone bidding sweep (non-cooperative): the grid regime's step (1) for an explicit bidder list.  Used for
 // kernel-level parity (bit-exact (jbest, bid) against the oracle) and for the HBM-roofline measurement of the CSR sweep.
 // ----------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SSLAPB_SWEEP_THREADS, 1) sslapb_bid_sweep_kernel(SslapbAuctionParams P, const int *bidders, int nb,
+__global__ void __launch_bounds__(1024, 1) sslapb_bid_sweep_kernel(SslapbAuctionParams P, const int *bidders, int nb,
                                                                   float eps_f, int merge)
 {
     const int lane = threadIdx.x & 31;
@@ -1140,14 +1087,24 @@ __global__ void __launch_bounds__(SSLAPB_SWEEP_THREADS, 1) sslapb_bid_sweep_kern
     const float spread = __double2float_ru(sslapb_key2double(P.ctrl->pmax_key) - pmin);
     int n2nd = 0;
     merge &= 1;
-    sweep_positions(P, const_cast<int *>(bidders), nullptr, nb, gwarp, nwarps, lane, eps, pmin, spread, prune, n2nd,
-                    [&](int a, int j, double bid) {
-                        if (lane == 0) {
-                            P.bidj[a] = j;
-                            P.bidv[a] = bid;
-                            if (merge && j >= 0) atomicMax(P.bidkey + j, sslapb_ord64(bid));
-                        }
-                    });
+    // plain loop at full occupancy: the kernel is instruction-issue bound, a software pipeline across rows buys nothing
+    for (int a = gwarp; a < nb; a += nwarps) {
+        const int i = bidders ? bidders[a] : a;
+        const long long st = __ldg(P.rowptr + i), en = __ldg(P.rowptr + i + 1);
+        int j; double bid;
+        if (prune && (((en + 3) >> 2) - (st >> 2)) <= 32) {
+            const SslapbStreamChunk c = sslapb_stream_chunk(P.cols, P.vals, st, en, lane);
+            const SslapbBid o = row_bid_pruned(c, P.price, st, en, lane, eps, pmin, spread, n2nd);
+            j = o.j; bid = o.bid;
+        } else {
+            row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);
+        }
+        if (lane == 0) {
+            P.bidj[a] = j;
+            P.bidv[a] = bid;
+            if (merge && j >= 0) atomicMax(P.bidkey + j, sslapb_ord64(bid));
+        }
+    }
     if (n2nd && lane == 0) atomicAdd((unsigned long long *)&P.ctrl->prune_second_pass, (unsigned long long)n2nd);
 }
 
@@ -1209,7 +1166,7 @@ extern "C" cudaError_t sslapb_launch_price_bounds(const SslapbAuctionParams *P, 
 extern "C" cudaError_t sslapb_launch_bid_sweep(const SslapbAuctionParams *P, const int *bidders, int nb, float eps,
                                                int merge, int grid, cudaStream_t stream)
 {
-    sslapb_bid_sweep_kernel<<<grid, SSLAPB_SWEEP_THREADS, 0, stream>>>(*P, bidders, nb, eps, merge);
+    sslapb_bid_sweep_kernel<<<grid, 1024, 0, stream>>>(*P, bidders, nb, eps, merge);
     return cudaGetLastError();
 }
 
