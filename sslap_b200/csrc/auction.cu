@@ -822,22 +822,37 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
     const int nthreads = nblk * blockDim.x;
     __shared__ int s_red;
     __shared__ int s_hpre[3];
+    __shared__ struct { int nu, done, nred, tie; float eps; long long its, max_iter; unsigned long long pmin0, pmin1, pmax; } s_top;
     unsigned bar_epoch = 0;                                    // barriers passed so far * #CTAs (wraps harmlessly)
 
     if (gtid == 0) C->t_begin = sslapb_globaltimer();
 
     for (;;) {
-        // ---- loop top: every CTA arrives here right after a grid barrier; the control block is stable
-        int nu = __shfl_sync(SSLAPB_FULL, *(volatile int *)&C->nu, 0);        // shuffles: warp-uniform for the compiler
-        int done = __shfl_sync(SSLAPB_FULL, *(volatile int *)&C->done, 0);
-        const float eps_f = *(volatile float *)&C->eps;
-        const long long its = *(volatile long long *)&C->its;
-        const long long max_iter = *(volatile long long *)&C->max_iter;
-        const int phase_slot = (*(volatile int *)&C->nreductions) & 1;
+        // ---- loop top: every CTA arrives here right after a grid barrier; the control block is stable.  ONE thread per
+        // CTA reads it (all 75k threads loading the same line serialise in its L2 slice) and shares it through smem.
+        if (tid == 0) {
+            s_top.nu = *(volatile int *)&C->nu;
+            s_top.done = *(volatile int *)&C->done;
+            s_top.eps = *(volatile float *)&C->eps;
+            s_top.its = *(volatile long long *)&C->its;
+            s_top.max_iter = *(volatile long long *)&C->max_iter;
+            s_top.nred = *(volatile int *)&C->nreductions;
+            s_top.pmin0 = *(volatile unsigned long long *)&C->pmin_key[0];
+            s_top.pmin1 = *(volatile unsigned long long *)&C->pmin_key[1];
+            s_top.pmax = *(volatile unsigned long long *)&C->pmax_key;
+        }
+        __syncthreads();
+        int nu = __shfl_sync(SSLAPB_FULL, s_top.nu, 0);        // shuffles: warp-uniform for the compiler
+        int done = __shfl_sync(SSLAPB_FULL, s_top.done, 0);
+        const float eps_f = s_top.eps;
+        const long long its = s_top.its;
+        const long long max_iter = s_top.max_iter;
+        const int phase_slot = s_top.nred & 1;
         // price bounds for the pruned sweep, taken at the start of the eps-phase: pmin stays a valid lower bound all phase
         // long (prices never decrease); the spread is only a heuristic for which candidates to gather first
-        const double pmin = sslapb_key2double(*(volatile unsigned long long *)&C->pmin_key[phase_slot]);
-        const float spread = __double2float_ru(sslapb_key2double(*(volatile unsigned long long *)&C->pmax_key) - pmin) + 2.0f * eps_f;
+        const double pmin = sslapb_key2double(phase_slot ? s_top.pmin1 : s_top.pmin0);
+        const float spread = __double2float_ru(sslapb_key2double(s_top.pmax) - pmin) + 2.0f * eps_f;
+        __syncthreads();                                       // s_top is rewritten only after every thread has read it
         if (done) break;
 
         if (nu > P.t_small) {
@@ -879,7 +894,9 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
             if (gtid == 0) tp1 = sslapb_globaltimer();
             GB();
             if (gtid == 0) tp2 = sslapb_globaltimer();
-            const int tie = __shfl_sync(SSLAPB_FULL, *(volatile int *)&C->tie_flag, 0);
+            if (tid == 0) s_top.tie = *(volatile int *)&C->tie_flag;
+            __syncthreads();
+            const int tie = __shfl_sync(SSLAPB_FULL, s_top.tie, 0);
             const int L = (nu + (int)nblk - 1) / (int)nblk;    // each CTA owns a contiguous chunk of positions
             const int lo = min(nu, (int)blockIdx.x * L), hi = min(nu, lo + L);
             if (tie) {                                         // (1b) equal best bids: earliest list position wins (:379)
@@ -985,8 +1002,11 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
             GB();
         }
 
-        nu = __shfl_sync(SSLAPB_FULL, *(volatile int *)&C->nu, 0);
-        done = __shfl_sync(SSLAPB_FULL, *(volatile int *)&C->done, 0);
+        if (tid == 0) { s_top.nu = *(volatile int *)&C->nu; s_top.done = *(volatile int *)&C->done; }
+        __syncthreads();
+        nu = __shfl_sync(SSLAPB_FULL, s_top.nu, 0);
+        done = __shfl_sync(SSLAPB_FULL, s_top.done, 0);
+        __syncthreads();
         if (done || nu != 0) continue;
 
         // ================================ full assignment reached: terminate() / eps-scaling (:275-292) ================================
