@@ -578,9 +578,9 @@ __device__ __forceinline__ int chain_rounds(const SslapbAuctionParams &P, double
         SslapbBid B;
         SslapbChunk nxt;
         bool nsingle = false;
-        if (single) {
-            if (!sweep_single(P, cur, lst, ldg, eps, its + 1 < max_iter, B, nxt, nsingle)) { done = 4; break; }
-        } else {                                               // long row: generic sweep, nothing prefetched
+        bool lean = single;
+        if (lean) lean = sweep_single(P, cur, lst, ldg, eps, its + 1 < max_iter, B, nxt, nsingle);
+        if (!lean) {                                           // long row, or every candidate at -inf: exact generic sweep
             B = row_bid_rec<32>(P.cols, P.vals, P.rec, lst, lst + ldg, lane, eps);
             if (B.j < 0) { done = 4; break; }
             const long long n0 = B.pstart >> 2, n1 = (B.pstart + B.pdeg + 3) >> 2;
@@ -632,10 +632,9 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
         SslapbChunk nxt = cur;
         bool nsingle = false;
         if (active) {
-            bool ok;
-            if (single) {
-                ok = sweep_single(P, cur, st, dg, eps, true, B, nxt, nsingle);
-            } else {
+            bool ok = single;
+            if (ok) ok = sweep_single(P, cur, st, dg, eps, true, B, nxt, nsingle);
+            if (!ok) {                                         // long row, or every candidate at -inf: exact generic sweep
                 B = row_bid_rec<32>(P.cols, P.vals, P.rec, st, st + dg, lane, eps);
                 ok = B.j >= 0;
                 const long long n0 = B.pstart >> 2, n1 = (B.pstart + B.pdeg + 3) >> 2;
@@ -885,6 +884,8 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
                     const SslapbStreamChunk c = sslapb_stream_chunk(P.cols, P.vals, st, en, lane);
                     const SslapbBid o = row_bid_pruned(c, P.price, st, en, lane, eps, pmin, spread, n2nd);
                     j = o.j; bid = o.bid;
+                    // every candidate at -inf (objects priced +inf by single-choice bidders): the exact generic sweep decides
+                    if (j < 0) row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);
                 } else {
                     row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);
                 }
@@ -1116,6 +1117,7 @@ __global__ void __launch_bounds__(1024, 1) sslapb_bid_sweep_kernel(SslapbAuction
             const SslapbStreamChunk c = sslapb_stream_chunk(P.cols, P.vals, st, en, lane);
             const SslapbBid o = row_bid_pruned(c, P.price, st, en, lane, eps, pmin, spread, n2nd);
             j = o.j; bid = o.bid;
+            if (j < 0) row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);   // all candidates at -inf
         } else {
             row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);
         }
@@ -1268,6 +1270,7 @@ __global__ void __launch_bounds__(128) sslapb_auction_batch_kernel(SslapbBatchPa
                 const SslapbStreamChunk c = sslapb_stream_chunk(B.cols, B.vals, st, en, lane);
                 const SslapbBid o = row_bid_pruned(c, B.price, st, en, lane, epsd, 0.0, __int_as_float(0x7f800000), dummy2nd);
                 j = o.j; bid = o.bid;
+                if (j < 0) row_bid<32>(B.cols, B.vals, B.price, st, en, lane, epsd, j, bid);   // all candidates at -inf
             } else {
                 row_bid<32>(B.cols, B.vals, B.price, st, en, lane, epsd, j, bid);
             }
