@@ -28,11 +28,10 @@ cudaError_t sslapb_auction_grid_size(int, int *);
 cudaError_t sslapb_launch_bid_sweep(const SslapbAuctionParams *, const int *, int, float, int, int, cudaStream_t);
 cudaError_t sslapb_launch_price_bounds(const SslapbAuctionParams *, cudaStream_t);
 cudaError_t sslapb_hk_launch_greedy(const long long *, const int *, int, int *, int *, SslapbHkFlags *, int, cudaStream_t);
-cudaError_t sslapb_hk_launch_phase_init(int, int, const int *, int *, int *, SslapbHkFlags *, int, cudaStream_t);
-cudaError_t sslapb_hk_launch_bfs_level(const long long *, const int *, int, int, const int *, int *, SslapbHkFlags *, int,
-                                       cudaStream_t);
-cudaError_t sslapb_hk_launch_augment(const long long *, const int *, int, int, int *, int *, int *, int *, long long *,
-                                     int *, SslapbHkFlags *, int, cudaStream_t);
+cudaError_t sslapb_hk_launch_phase_init(int, int, const int *, int *, int *, int *, int *, SslapbHkFlags *, int, cudaStream_t);
+cudaError_t sslapb_hk_launch_bfs_level(const long long *, const int *, int, int, const int *, int *, int *, int *, int *,
+                                       SslapbHkFlags *, int, cudaStream_t);
+cudaError_t sslapb_hk_launch_augment(int, const int *, const int *, int *, int *, SslapbHkFlags *, int, cudaStream_t);
 }
 
 struct SslapbBatchMeta {
@@ -305,12 +304,13 @@ static int run_hopcroft(sslapb_handle *h, int32_t *card_out)
 {
     const int N = h->N, M = h->M;
     CK(h->pair_u.reserve((size_t)N * 4)); CK(h->pair_v.reserve((size_t)M * 4));
-    CK(h->dist.reserve((size_t)N * 4)); CK(h->visited.reserve((size_t)M * 4));
-    CK(h->cursor.reserve((size_t)N * 8)); CK(h->pred.reserve((size_t)N * 4));
+    CK(h->dist.reserve((size_t)N * 4)); CK(h->visited.reserve((size_t)M * 4));      // visited = pred_v
+    CK(h->cursor.reserve((size_t)N * 8)); CK(h->pred.reserve((size_t)N * 4));         // cursor = root | end_of_root
     CK(h->hkflags.reserve(sizeof(SslapbHkFlags)));
     const long long *rowptr = h->rowptr.as<long long>();
     const int *cols = h->cols.as<int>();
     SslapbHkFlags *dF = h->hkflags.as<SslapbHkFlags>();
+    int *root = h->cursor.as<int>(), *end_of_root = h->cursor.as<int>() + N, *pred_v = h->visited.as<int>();
     CK(cudaMemsetAsync(h->pair_u.p, 0xff, (size_t)N * 4, h->stream));
     CK(cudaMemsetAsync(h->pair_v.p, 0xff, (size_t)M * 4, h->stream));
     CK(cudaMemsetAsync(dF, 0, sizeof(SslapbHkFlags), h->stream));
@@ -320,25 +320,29 @@ static int run_hopcroft(sslapb_handle *h, int32_t *card_out)
     CK(cudaStreamSynchronize(h->stream));
     long long matching = F.matched;
     const long long bound = N < M ? N : M;
+    const bool trace = getenv("SSLAPB_HK_TRACE") != nullptr;
+    if (trace) fprintf(stderr, "hk greedy: matched=%lld of %lld\n", matching, bound);
     while (matching < bound) {
-        CK(sslapb_hk_launch_phase_init(N, M, h->pair_u.as<int>(), h->dist.as<int>(), h->visited.as<int>(), dF, h->sms, h->stream));
-        int level = 0, dist_nil = -1;
-        for (;;) {
+        CK(sslapb_hk_launch_phase_init(N, M, h->pair_u.as<int>(), h->dist.as<int>(), root, end_of_root, pred_v, dF, h->sms, h->stream));
+        int level = 0;
+        bool found = false;
+        for (;;) {                                            // level-synchronous BFS (feasibility_.pyx:128-168)
             CK(cudaMemsetAsync(&dF->grew, 0, sizeof(int), h->stream));
-            CK(sslapb_hk_launch_bfs_level(rowptr, cols, N, level, h->pair_v.as<int>(), h->dist.as<int>(), dF, h->sms, h->stream));
+            CK(sslapb_hk_launch_bfs_level(rowptr, cols, N, level, h->pair_v.as<int>(), h->dist.as<int>(), root, end_of_root,
+                                          pred_v, dF, h->sms, h->stream));
             CK(cudaMemcpyAsync(&F, dF, sizeof F, cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
-            if (F.found) { dist_nil = level + 1; break; }
+            if (F.found) { found = true; break; }
             if (!F.grew) break;
             ++level;
         }
-        if (dist_nil < 0) break;                              // no augmenting path: maximum (feasibility_.pyx:202-203)
-        CK(sslapb_hk_launch_augment(rowptr, cols, N, dist_nil, h->pair_u.as<int>(), h->pair_v.as<int>(), h->dist.as<int>(),
-                                    h->visited.as<int>(), h->cursor.as<long long>(), h->pred.as<int>(), dF, h->sms, h->stream));
+        if (!found) break;                                    // no augmenting path: maximum (feasibility_.pyx:202-203)
+        CK(sslapb_hk_launch_augment(N, end_of_root, pred_v, h->pair_u.as<int>(), h->pair_v.as<int>(), dF, h->sms, h->stream));
         CK(cudaMemcpyAsync(&F, dF, sizeof F, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         if (F.augmented <= 0) return fail(h, SSLAPB_E_ABORTED, "Hopcroft-Karp phase made no progress (internal error)");
         matching += F.augmented;
+        if (trace) fprintf(stderr, "hk phase: levels=%d augmented=%d matching=%lld/%lld\n", level + 1, F.augmented, matching, bound);
     }
     *card_out = (int32_t)matching;
     return SSLAPB_OK;
@@ -421,7 +425,6 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
         meta->n_rows = h->N; meta->n_cols = h->M; meta->nnz = h->nnz;
         meta->rounds_grid = c.rounds_grid; meta->rounds_warp = c.rounds_warp; meta->rounds_solo = c.rounds_solo;
         for (int k = 0; k < 8; ++k) meta->prof_ms[k] = (float)((double)c.prof[k] * 1e-6);
-        if (getenv("SSLAPB_PRINT_PROF2")) { fprintf(stderr, "prof2:"); for (int k = 0; k < 8; ++k) fprintf(stderr, " %llu", c.prof2[k]); fprintf(stderr, "\n"); }
         meta->stop_reason = c.done;
         meta->prune_second_pass = c.prune_second_pass;
         (void)assigned;

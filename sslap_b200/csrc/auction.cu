@@ -17,19 +17,6 @@
 //   solo  (nu <= 4)     : warp 0 of CTA 0 only; 32/16/8 lanes per bidder; no block barrier at all.
 #include "auction.cuh"
 
-#ifdef SSLAPB_PROFILE_SOLO
-// Diagnostic build only: cycle stamps inside the single-bidder round (the stamp waits for `dep` through a control dependency).
-__device__ __forceinline__ long long sslapb_clk_after(int dep)
-{
-    if (dep == 0x7ffffff1) __trap();
-    long long t;
-    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory");
-    return t;
-}
-#define SSLAPB_PROBE(K_, DEP_) do { if (acc) { const long long t_ = sslapb_clk_after((int)(DEP_)); acc[K_] += t_ - tprev; tprev = t_; } } while (0)
-#else
-#define SSLAPB_PROBE(K_, DEP_) do { } while (0)
-#endif
 #define SSLAPB_THREADS 512       // persistent kernel: one CTA of 16 warps per SM (128 registers per thread)
 
 // ----------------------------------------------------------------------------------------------------------------------
@@ -75,12 +62,8 @@ __device__ __forceinline__ unsigned sslapb_group_mask()
 template <int W, bool REC>
 __device__ __forceinline__ SslapbBid row_bid_core(const int *__restrict__ cols, const double *__restrict__ vals,
                                                   const double *price, const SslapbObjRec *rec, long long start,
-                                                  long long end, int t, double eps, long long *acc = nullptr)
+                                                  long long end, int t, double eps)
 {
-#ifdef SSLAPB_PROFILE_SOLO
-    long long tprev = 0;
-    if (acc) tprev = sslapb_clk_after(t);
-#endif
     const int4 *c4 = reinterpret_cast<const int4 *>(cols);
     const double2 *v2 = reinterpret_cast<const double2 *>(vals);
     unsigned long long b = 0ull, s = 0ull;          // best / second-best key of this lane (0 = none)
@@ -100,7 +83,6 @@ __device__ __forceinline__ SslapbBid row_bid_core(const int *__restrict__ cols, 
         const double2 vb = REC ? __ldg(v2 + 2 * ch + 1) : sslapb_ldg_stream_d2(v2 + 2 * ch + 1);
         const int lo = (int)(start - (ch << 2)), hi = (int)min(end - (ch << 2), 4ll);
         const bool m0 = (0 >= lo) & (0 < hi), m1 = (1 >= lo) & (1 < hi), m2 = (2 >= lo) & (2 < hi), m3 = (3 >= lo) & (3 < hi);
-        SSLAPB_PROBE(0, cj.x ^ __double2hiint(va.x) ^ __double2hiint(vb.y));
         double p0, p1, p2, p3;
         int4 r0, r1, r2, r3;
         if (REC) {
@@ -113,7 +95,6 @@ __device__ __forceinline__ SslapbBid row_bid_core(const int *__restrict__ cols, 
             p1 = m1 ? rec[cj.y].price : 0.0;
             p2 = m2 ? rec[cj.z].price : 0.0;
             p3 = m3 ? rec[cj.w].price : 0.0;
-            SSLAPB_PROBE(1, r0.z ^ r1.z ^ r2.z ^ r3.z ^ __double2hiint(p0) ^ __double2hiint(p1) ^ __double2hiint(p2) ^ __double2hiint(p3));
         } else {
             p0 = m0 ? price[cj.x] : 0.0;
             p1 = m1 ? price[cj.y] : 0.0;
@@ -140,7 +121,6 @@ __device__ __forceinline__ SslapbBid row_bid_core(const int *__restrict__ cols, 
         } else {
             s = b4 > s ? b4 : s;
         }
-        SSLAPB_PROBE(2, bi ^ (int)b ^ (int)s);
     }
     // cross-lane: lexicographic max of (key, row index) and the second-largest key, on the redux unit
     const unsigned gm = sslapb_group_mask<W>();
@@ -171,7 +151,6 @@ __device__ __forceinline__ SslapbBid row_bid_core(const int *__restrict__ cols, 
     }
     const double wi = skey ? sslapb_key2double(skey) : SSLAPB_NEG_INF;   // w_i = -inf for a single-entry row (:344)
     o.bid = (bc - wi) + eps;                                   // :360
-    SSLAPB_PROBE(3, o.j ^ o.powner ^ o.pdeg ^ __double2hiint(o.bid) ^ (int)o.pstart);
     return o;
 }
 
@@ -332,9 +311,9 @@ __device__ __forceinline__ void row_bid(const int *__restrict__ cols, const doub
 template <int W>
 __device__ __noinline__ SslapbBid row_bid_rec(const int *__restrict__ cols, const double *__restrict__ vals,
                                               const SslapbObjRec *rec, long long start, long long end, int t,
-                                              double eps, long long *acc = nullptr)
+                                              double eps)
 {
-    return row_bid_core<W, true>(cols, vals, nullptr, rec, start, end, t, eps, acc);
+    return row_bid_core<W, true>(cols, vals, nullptr, rec, start, end, t, eps);
 }
 
 // eCE / objective sweep of one row by a full warp (auction_.pyx:460-483 and :504-521).
@@ -619,13 +598,6 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
         single = (((st + dg + 3) >> 2) - (st >> 2)) <= 32;
         cur = sslapb_load_chunk(P.cols, P.vals, (st >> 2) + lane, single && ((st >> 2) + lane < ((st + dg + 3) >> 2)));
     }
-#ifdef SSLAPB_PROFILE_SOLO
-    long long pq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define MQ(K_, DEP_) do { const long long t_ = sslapb_clk_after((int)(DEP_)); pq[K_] += t_ - tq; tq = t_; } while (0)
-    long long tq = sslapb_clk_after(nu);
-#else
-#define MQ(K_, DEP_) do { } while (0)
-#endif
     while (nu > 1 && nu <= SSLAPB_THREADS / 32 && !done) {
         SslapbBid B;
         B.j = -1; B.bid = 0.0; B.powner = -1; B.pdeg = 0; B.pstart = 0;
@@ -644,9 +616,7 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
             if (!ok) { B.j = -1; done = 4; }
             if (lane == 0) { s_j[a] = B.j; s_bidv[a] = B.bid; }
         }
-        MQ(0, B.j ^ __double2hiint(B.bid) ^ B.powner);
         __syncthreads();
-        MQ(1, s_j[lane & 15]);
         int nme = me; long long nst = st; int ndg = dg; bool won = false;
         if (active) {                                          // merge (:375-385): do I hold the best bid on my object?
             const int oj = lane < nu ? s_j[lane] : -1;
@@ -662,9 +632,7 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
         if (__any_sync(SSLAPB_FULL, lane < nu && s_j[lane] < 0)) done = 4;   // uniform across the CTA (same smem)
         ++its; ++rounds;
         if (its >= max_iter && !done) done = 3;
-        MQ(2, (int)won ^ nme ^ done);
         __syncthreads();
-        MQ(3, s_list[lane & 15]);
         // compaction (:429-430), identical in every warp
         const int v = lane < nu ? s_list[lane] : 0;
         const unsigned holes = __ballot_sync(SSLAPB_FULL, lane < nu && v < 0);
@@ -695,14 +663,7 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
             me = -1;
         }
         // no third barrier: s_list / s_j are rewritten only after the next round's first barrier / after this round's second
-        MQ(4, me ^ nu ^ cur.cj.x ^ __double2hiint(cur.vb.y));
-#ifdef SSLAPB_PROFILE_SOLO
-        pq[5] += 1; pq[6] += nu;
-#endif
     }
-#ifdef SSLAPB_PROFILE_SOLO
-    if (threadIdx.x == 0) for (int k = 0; k < 8; ++k) P.ctrl->prof2[k] += (unsigned long long)pq[k];
-#endif
     return nu;
 }
 
