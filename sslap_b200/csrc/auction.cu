@@ -553,13 +553,12 @@ __device__ __forceinline__ int chain_rounds(const SslapbAuctionParams &P, double
     int nu = 1;
     bool single = (((lst + ldg + 3) >> 2) - (lst >> 2)) <= 32;
     SslapbChunk cur = sslapb_load_chunk(P.cols, P.vals, (lst >> 2) + lane, single && ((lst >> 2) + lane < ((lst + ldg + 3) >> 2)));
-    while (nu == 1 && !done) {
+    while (nu == 1 && !done && single) {                       // long rows are swept by the whole CTA (coop_chain_rounds)
         SslapbBid B;
         SslapbChunk nxt;
         bool nsingle = false;
-        bool lean = single;
-        if (lean) lean = sweep_single(P, cur, lst, ldg, eps, its + 1 < max_iter, B, nxt, nsingle);
-        if (!lean) {                                           // long row, or every candidate at -inf: exact generic sweep
+        const bool lean = sweep_single(P, cur, lst, ldg, eps, its + 1 < max_iter, B, nxt, nsingle);
+        if (!lean) {                                           // every candidate at -inf: exact generic sweep
             B = row_bid_rec<32>(P.cols, P.vals, P.rec, lst, lst + ldg, lane, eps);
             if (B.j < 0) { done = 4; break; }
             const long long n0 = B.pstart >> 2, n1 = (B.pstart + B.pdeg + 3) >> 2;
@@ -667,6 +666,155 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
     return nu;
 }
 
+// ---- long rows (more than one warp pass, e.g. dense inputs) in the single-bidder chain: the WHOLE CTA sweeps the row,
+// warp w taking the 32-chunk trips w, w+16, ...; the per-warp top-2 go through shared memory and warp 0 combines them,
+// commits and publishes the next bidder.  Two block barriers per round, independent of the row length up to 2048 entries
+// per pass (a 10^4-entry row takes 5 trips per warp instead of 79 dependent trips on one warp).
+struct SslapbPartial {
+    unsigned long long bk, sk;    // best / second-best key seen by this warp (0 = none)
+    double bc;                    // value a_ij of the best entry
+    int bi, bj;                   // its row index / column
+    int4 br;                      // its object's record {start lo, start hi, owner, deg}
+};
+struct SslapbCoopRow { long long st; int me, dg, state; };   // state: 0 next row is long, 1 short, 2 frontier empty, 3 max_iter, 4 abort
+
+__device__ __forceinline__ SslapbPartial row_partial_rec(const int *__restrict__ cols, const double *__restrict__ vals,
+                                                         const SslapbObjRec *rec, long long start, long long end, int lane,
+                                                         int trip0, int tstride)
+{
+    const int4 *c4 = reinterpret_cast<const int4 *>(cols);
+    const double2 *v2 = reinterpret_cast<const double2 *>(vals);
+    unsigned long long b = 0ull, s = 0ull;
+    double bc = 0.0;
+    int bi = -1, bj = -1;
+    int4 br = make_int4(0, 0, -1, 0);
+    const long long c0 = start >> 2, c1 = (end + 3) >> 2;
+    const int trips = (int)((c1 - c0 + 31) >> 5);
+#pragma unroll 1
+    for (int it = trip0; it < trips; it += tstride) {
+        const long long ch = c0 + (long long)it * 32 + lane;
+        if (ch >= c1) continue;
+        const int4 cj = __ldg(c4 + ch);
+        const double2 va = __ldg(v2 + 2 * ch), vb = __ldg(v2 + 2 * ch + 1);
+        const int lo = (int)(start - (ch << 2)), hi = (int)min(end - (ch << 2), 4ll);
+        const bool m0 = (0 >= lo) & (0 < hi), m1 = (1 >= lo) & (1 < hi), m2 = (2 >= lo) & (2 < hi), m3 = (3 >= lo) & (3 < hi);
+        SslapbRec256 q0, q1, q2, q3;
+        q0.start = q1.start = q2.start = q3.start = 0ull;
+        q0.owner_deg = q1.owner_deg = q2.owner_deg = q3.owner_deg = 0xffffffffull;
+        q0.price_bits = q1.price_bits = q2.price_bits = q3.price_bits = 0ull;
+        if (m0) q0 = sslapb_ld_rec256(rec + cj.x);
+        if (m1) q1 = sslapb_ld_rec256(rec + cj.y);
+        if (m2) q2 = sslapb_ld_rec256(rec + cj.z);
+        if (m3) q3 = sslapb_ld_rec256(rec + cj.w);
+        const unsigned long long k0 = sslapb_vkey(va.x, __longlong_as_double((long long)q0.price_bits), m0);
+        const unsigned long long k1 = sslapb_vkey(va.y, __longlong_as_double((long long)q1.price_bits), m1);
+        const unsigned long long k2 = sslapb_vkey(vb.x, __longlong_as_double((long long)q2.price_bits), m2);
+        const unsigned long long k3 = sslapb_vkey(vb.y, __longlong_as_double((long long)q3.price_bits), m3);
+        const bool w01 = k1 >= k0, w23 = k3 >= k2;
+        const unsigned long long b01 = w01 ? k1 : k0, l01 = w01 ? k0 : k1;
+        const unsigned long long b23 = w23 ? k3 : k2, l23 = w23 ? k2 : k3;
+        const bool wf = b23 >= b01;
+        const unsigned long long b4 = wf ? b23 : b01;
+        const unsigned long long s4 = wf ? (b01 > l23 ? b01 : l23) : (b23 > l01 ? b23 : l01);
+        const int w4 = wf ? (w23 ? 3 : 2) : (w01 ? 1 : 0);
+        if (b4 >= b && b4 != 0ull) {                           // later trips hold later entries: they win equal keys (:351)
+            s = b > s4 ? b : s4;
+            b = b4;
+            bi = (int)((ch << 2) - start) + w4;
+            bc = (w4 & 2) ? ((w4 & 1) ? vb.y : vb.x) : ((w4 & 1) ? va.y : va.x);
+            bj = (w4 & 2) ? ((w4 & 1) ? cj.w : cj.z) : ((w4 & 1) ? cj.y : cj.x);
+            const SslapbRec256 &q = (w4 & 2) ? ((w4 & 1) ? q3 : q2) : ((w4 & 1) ? q1 : q0);
+            br = make_int4((int)q.start, (int)(q.start >> 32), (int)q.owner_deg, (int)(q.owner_deg >> 32));
+        } else {
+            s = b4 > s ? b4 : s;
+        }
+    }
+    // warp-level top-2 (keys) + payload of the winning lane
+    const unsigned bh = (unsigned)(b >> 32), bl = (unsigned)b;
+    const unsigned hi = __reduce_max_sync(SSLAPB_FULL, bh);
+    const unsigned lo = __reduce_max_sync(SSLAPB_FULL, bh == hi ? bl : 0u);
+    const bool top = (bh == hi) & (bl == lo);
+    const int widx = __reduce_max_sync(SSLAPB_FULL, top ? bi : -1);
+    const bool iswin = top & (bi == widx) & (bi >= 0);
+    const unsigned long long cand = iswin ? s : b;
+    const unsigned chh = (unsigned)(cand >> 32), chl = (unsigned)cand;
+    const unsigned shi = __reduce_max_sync(SSLAPB_FULL, chh);
+    const unsigned slo = __reduce_max_sync(SSLAPB_FULL, chh == shi ? chl : 0u);
+    const unsigned own = __ballot_sync(SSLAPB_FULL, iswin);
+    const int src = own ? (__ffs(own) - 1) : lane;
+    SslapbPartial o;
+    o.bk = own ? (((unsigned long long)hi << 32) | lo) : 0ull;
+    o.sk = ((unsigned long long)shi << 32) | slo;
+    o.bi = own ? widx : -1;
+    o.bc = __shfl_sync(SSLAPB_FULL, bc, src);
+    o.bj = __shfl_sync(SSLAPB_FULL, bj, src);
+    o.br.x = __shfl_sync(SSLAPB_FULL, br.x, src); o.br.y = __shfl_sync(SSLAPB_FULL, br.y, src);
+    o.br.z = __shfl_sync(SSLAPB_FULL, br.z, src); o.br.w = __shfl_sync(SSLAPB_FULL, br.w, src);
+    return o;
+}
+
+// executed by ALL warps of CTA 0 while the single bidder's row is long; warp 0 carries the list entry in (li, lst, ldg)
+__device__ __forceinline__ int coop_chain_rounds(const SslapbAuctionParams &P, double eps, SslapbPartial *s_part,
+                                                 SslapbCoopRow *s_row, int &li, long long &lst, int &ldg, long long &its,
+                                                 long long max_iter, int &done, long long &rounds)
+{
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(SSLAPB_FULL, (int)(threadIdx.x >> 5), 0);
+    constexpr int NW = SSLAPB_THREADS / 32;
+    int nu = 1;
+    for (;;) {
+        const long long st = s_row->st;
+        const int dg = s_row->dg;
+        const SslapbPartial part = row_partial_rec(P.cols, P.vals, P.rec, st, st + dg, lane, warp, NW);
+        if (lane == 0) s_part[warp] = part;
+        __syncthreads();
+        if (warp == 0) {
+            SslapbPartial q;
+            q.bk = 0ull; q.sk = 0ull; q.bc = 0.0; q.bi = -1; q.bj = -1; q.br = make_int4(0, 0, -1, 0);
+            if (lane < NW) q = s_part[lane];
+            const unsigned bh = (unsigned)(q.bk >> 32), bl = (unsigned)q.bk;
+            const unsigned hi = __reduce_max_sync(SSLAPB_FULL, bh);
+            const unsigned lo = __reduce_max_sync(SSLAPB_FULL, bh == hi ? bl : 0u);
+            const bool top = (bh == hi) & (bl == lo);
+            const int widx = __reduce_max_sync(SSLAPB_FULL, top ? q.bi : -1);
+            const bool iswin = top & (q.bi == widx) & (q.bi >= 0);
+            const unsigned long long cand = iswin ? q.sk : q.bk;
+            const unsigned chh = (unsigned)(cand >> 32), chl = (unsigned)cand;
+            const unsigned shi = __reduce_max_sync(SSLAPB_FULL, chh);
+            const unsigned slo = __reduce_max_sync(SSLAPB_FULL, chh == shi ? chl : 0u);
+            const unsigned long long skey = ((unsigned long long)shi << 32) | slo;
+            const unsigned own = __ballot_sync(SSLAPB_FULL, iswin);
+            int state;
+            if (own == 0u) { state = 4; done = 4; }            // empty row: rejected at CSR build, cannot happen
+            else {
+                const int src = __ffs(own) - 1;
+                SslapbBid B;
+                const double bc = __shfl_sync(SSLAPB_FULL, q.bc, src);
+                B.j = __shfl_sync(SSLAPB_FULL, q.bj, src);
+                const int sx = __shfl_sync(SSLAPB_FULL, q.br.x, src), sy = __shfl_sync(SSLAPB_FULL, q.br.y, src);
+                B.powner = __shfl_sync(SSLAPB_FULL, q.br.z, src);
+                B.pdeg = __shfl_sync(SSLAPB_FULL, q.br.w, src);
+                B.pstart = (long long)(((unsigned long long)(unsigned)sy << 32) | (unsigned)sx);
+                const double wi = skey > SSLAPB_KEY_NEG_INF ? sslapb_key2double(skey) : SSLAPB_NEG_INF;   // :344
+                B.bid = (bc - wi) + eps;                       // :360
+                if (lane == 0) commit_win(P, li, lst, ldg, B); // the only bidder wins (:379-385, :394-427)
+                __syncwarp();
+                ++its; ++rounds;
+                if (B.powner < 0) { nu = 0; li = -1; state = 2; }
+                else {
+                    li = B.powner; lst = B.pstart; ldg = B.pdeg;
+                    state = ((((lst + ldg + 3) >> 2) - (lst >> 2)) > 32) ? 0 : 1;
+                }
+                if (its >= max_iter) { done = 3; state = 3; }
+            }
+            if (lane == 0) { s_row->st = lst; s_row->dg = ldg; s_row->me = li; s_row->state = state; }
+        }
+        __syncthreads();
+        if (s_row->state != 0) break;
+        __syncthreads();                                       // s_row is rewritten only after everybody has read the state
+    }
+    return nu;
+}
+
 // CTA 0 finishes the eps-phase alone once nu <= t_small (nu only shrinks inside a phase).
 __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, SslapbCtrl *C, int nu, float eps_f,
                                              long long its, long long max_iter)
@@ -677,6 +825,8 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
     __shared__ SslapbBid s_bid[32];
     __shared__ int s_nu, s_done;
     __shared__ long long s_its, s_rw, s_rs;
+    __shared__ SslapbPartial s_part[SSLAPB_THREADS / 32];
+    __shared__ SslapbCoopRow s_row;
 
     // warp index through a shuffle: tells the compiler it is warp-uniform (same idiom as cutlass::canonical_warp_idx_sync)
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(SSLAPB_FULL, tid >> 5, 0);
@@ -721,12 +871,24 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
     if (nu > 1 && !done) nu = multi_rounds(P, eps, nu, s_list, s_start, s_deg, s_j, s_bidv, its, max_iter, done, rw, li, lst, ldg);
 
     unsigned long long tw1 = sslapb_globaltimer();
-    // ---- single-bidder chain: warp 0 alone, no block barrier (after multi_rounds warp a holds position a in registers)
-    if (warp == 0) {
-        if (nu == 1 && !done) nu = chain_rounds(P, eps, li, lst, ldg, its, max_iter, done, rs);
-        if (lane == 0) { s_nu = nu; s_done = done; s_its = its; s_rw = rw; s_rs = rs; }
+    // ---- single-bidder chain: warp 0 alone, no block barrier (after multi_rounds warp a holds position a in registers);
+    // whenever the bidder's row is longer than one warp pass the whole CTA sweeps it (coop_chain_rounds)
+    for (;;) {
+        if (warp == 0) {
+            if (nu == 1 && !done) nu = chain_rounds(P, eps, li, lst, ldg, its, max_iter, done, rs);
+            const bool longrow = nu == 1 && !done;             // chain_rounds stops in front of a long row
+            if (lane == 0) {
+                s_row.st = lst; s_row.dg = ldg; s_row.me = li; s_row.state = longrow ? 0 : 1;
+                s_nu = nu; s_done = done; s_its = its; s_rw = rw; s_rs = rs;
+            }
+        }
+        __syncthreads();
+        if (s_row.state != 0) break;
+        __syncthreads();
+        const int cnu = coop_chain_rounds(P, eps, s_part, &s_row, li, lst, ldg, its, max_iter, done, rs);
+        if (warp == 0) nu = cnu;
+        __syncthreads();
     }
-    __syncthreads();
     if (s_nu > 0 && warp < s_nu && lane == 0 && li >= 0 && (s_nu <= SSLAPB_THREADS / 32)) P.list[warp] = li;   // max_iter exit only
     if (tid == 0) {
         C->nu = s_nu;
