@@ -214,7 +214,7 @@ def main():
     avg = C.c_float(0)
     rc = L.sslapb_bid_sweep(h.ptr, None, None, N_ROWS, float(np.float32(1.0 / N_ROWS)), 1, 20, 1, None, None, C.byref(avg))
     assert rc == 0
-    sweep_bytes = 12 * nnz + 36 * N_ROWS                                   # 12 B per CSR entry + 36 B per bidder
+    sweep_bytes = 12 * nnz + 44 * N_ROWS                                   # 12 B per CSR entry + 44 B per bidder
     peak, peak_src = measured_peaks()
     achieved = sweep_bytes / (avg.value * 1e-3) / 1e9
 

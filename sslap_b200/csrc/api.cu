@@ -19,6 +19,7 @@ cudaError_t sslapb_launch_coo_ingest(const void *, const void *, int, long long,
                                      int *, double *, long long *, SslapbBuildFlags *, int, cudaStream_t);
 cudaError_t sslapb_launch_coo_sort(const void *, const void *, int, long long, const double *, long long, int, unsigned *,
                                    unsigned *, unsigned *, unsigned *, long long *, int *, int *, double *, int, cudaStream_t);
+cudaError_t sslapb_launch_rowmax(const long long *, const double *, long long, double *, int, cudaStream_t);
 cudaError_t sslapb_launch_index_max(const void *, const void *, int, long long, long long, long long *, int, cudaStream_t);
 cudaError_t sslapb_launch_dense_count(const double *, int, int, long long *, SslapbBuildFlags *, int, cudaStream_t);
 cudaError_t sslapb_launch_dense_fill(const double *, int, int, int, const long long *, int *, double *,
@@ -91,7 +92,7 @@ struct sslapb_handle {
     int N = 0, M = 0;
     long long nnz = 0;
     bool has_vals = false;
-    DevBuf stage_idx, stage_val, stage_mat, cols, vals, rowptr, flags;
+    DevBuf stage_idx, stage_val, stage_mat, cols, vals, rowptr, rowmax, flags;
     DevBuf sort_keys, sort_idx, sort_hist, sort_rows, sort_cols, sort_val;   // only for unsorted input
     DevBuf b_off, b_rows, b_cols, b_eps, b_meta, b_bad;                      // batched problems
     // auction state
@@ -142,7 +143,7 @@ extern "C" void sslapb_destroy(sslapb_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *all[] = {&h->b_off, &h->b_rows, &h->b_cols, &h->b_eps, &h->b_meta, &h->b_bad, &h->sort_keys, &h->sort_idx, &h->sort_hist, &h->sort_rows, &h->sort_cols, &h->sort_val, &h->stage_idx, &h->stage_val, &h->stage_mat, &h->cols, &h->vals, &h->rowptr, &h->flags, &h->price,
+    DevBuf *all[] = {&h->b_off, &h->b_rows, &h->b_cols, &h->b_eps, &h->b_meta, &h->b_bad, &h->sort_keys, &h->sort_idx, &h->sort_hist, &h->sort_rows, &h->sort_cols, &h->sort_val, &h->stage_idx, &h->stage_val, &h->stage_mat, &h->cols, &h->vals, &h->rowptr, &h->rowmax, &h->flags, &h->price,
                      &h->owner, &h->p2o, &h->list, &h->mover, &h->bidj, &h->bidv, &h->bidkey, &h->winpos,
                      &h->hole_count, &h->chosen, &h->ctrl, &h->bidders, &h->flush, &h->pair_u, &h->pair_v, &h->dist,
                      &h->visited, &h->cursor, &h->pred, &h->hkflags};
@@ -257,6 +258,10 @@ static int build_from_coo(sslapb_handle *h, const void *rows, const void *cols, 
         CK(cudaStreamSynchronize(h->stream));
         if (F.unsorted || F.out_of_range) return fail(h, SSLAPB_E_UNSORTED, "device sort failed (internal error)");
     }
+    if (val) {
+        CK(h->rowmax.reserve(((size_t)n_rows + 1) * sizeof(double)));
+        CK(sslapb_launch_rowmax(h->rowptr.as<long long>(), h->vals.as<double>(), n_rows, h->rowmax.as<double>(), h->sms, h->stream));
+    }
     return SSLAPB_OK;
 }
 
@@ -291,6 +296,10 @@ static int build_from_dense(sslapb_handle *h, const double *mat, int32_t n_rows,
                                 want_vals ? h->vals.as<double>() : nullptr, h->flags.as<SslapbBuildFlags>(), h->sms,
                                 h->stream));
     CK(cudaMemcpyAsync(&F, h->flags.p, sizeof F, cudaMemcpyDeviceToHost, h->stream));
+    if (want_vals) {
+        CK(h->rowmax.reserve(((size_t)n_rows + 1) * sizeof(double)));
+        CK(sslapb_launch_rowmax(h->rowptr.as<long long>(), h->vals.as<double>(), n_rows, h->rowmax.as<double>(), h->sms, h->stream));
+    }
     CK(cudaEventRecord(h->ev[2], h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->N = n_rows; h->M = n_cols; h->nnz = nnz; h->has_vals = want_vals;
@@ -360,6 +369,7 @@ static int reserve_auction_state(sslapb_handle *h, SslapbAuctionParams &P)
     CK(h->chosen.reserve(N * 8)); CK(h->ctrl.reserve(sizeof(SslapbCtrl)));
     P.N = h->N; P.M = h->M;
     P.rowptr = h->rowptr.as<long long>(); P.cols = h->cols.as<int>(); P.vals = h->vals.as<double>();
+    P.rowmax = h->rowmax.as<double>();
     P.price = h->price.as<double>(); P.rec = h->owner.as<SslapbObjRec>(); P.p2o = h->p2o.as<int>();
     P.list = h->list.as<int>(); P.mover = h->mover.as<int>(); P.bidj = h->bidj.as<int>(); P.bidv = h->bidv.as<double>();
     P.bidkey = h->bidkey.as<unsigned long long>(); P.winpos = h->winpos.as<int>();

@@ -62,8 +62,14 @@ __device__ __forceinline__ unsigned sslapb_group_mask()
 template <int W, bool REC>
 __device__ __forceinline__ SslapbBid row_bid_core(const int *__restrict__ cols, const double *__restrict__ vals,
                                                   const double *price, const SslapbObjRec *rec, long long start,
-                                                  long long end, int t, double eps)
+                                                  long long end, int t, double eps, double pmin = 0.0,
+                                                  double thr = -__builtin_huge_val())
 {
+    // (pmin, thr): bound pruning as in row_bid_pruned — entries with a < thr are not gathered; the uniform test
+    // fl(thr - pmin) < second-best proves them irrelevant, otherwise the row is swept again with thr = -inf.
+    SslapbBid o;
+#pragma unroll 1
+    for (int pass = 0;; ++pass) {
     const int4 *c4 = reinterpret_cast<const int4 *>(cols);
     const double2 *v2 = reinterpret_cast<const double2 *>(vals);
     unsigned long long b = 0ull, s = 0ull;          // best / second-best key of this lane (0 = none)
@@ -82,7 +88,8 @@ __device__ __forceinline__ SslapbBid row_bid_core(const int *__restrict__ cols, 
         const double2 va = REC ? __ldg(v2 + 2 * ch) : sslapb_ldg_stream_d2(v2 + 2 * ch);
         const double2 vb = REC ? __ldg(v2 + 2 * ch + 1) : sslapb_ldg_stream_d2(v2 + 2 * ch + 1);
         const int lo = (int)(start - (ch << 2)), hi = (int)min(end - (ch << 2), 4ll);
-        const bool m0 = (0 >= lo) & (0 < hi), m1 = (1 >= lo) & (1 < hi), m2 = (2 >= lo) & (2 < hi), m3 = (3 >= lo) & (3 < hi);
+        const bool m0 = (0 >= lo) & (0 < hi) & (va.x >= thr), m1 = (1 >= lo) & (1 < hi) & (va.y >= thr);
+        const bool m2 = (2 >= lo) & (2 < hi) & (vb.x >= thr), m3 = (3 >= lo) & (3 < hi) & (vb.y >= thr);
         double p0, p1, p2, p3;
         int4 r0, r1, r2, r3;
         if (REC) {
@@ -139,7 +146,6 @@ __device__ __forceinline__ SslapbBid row_bid_core(const int *__restrict__ cols, 
     const int src = own ? (__ffs(own) - 1) : (threadIdx.x & 31);
     bc = __shfl_sync(SSLAPB_FULL, bc, src);
     bj = __shfl_sync(SSLAPB_FULL, bj, src);
-    SslapbBid o;
     o.j = own ? bj : -1;
     if (REC) {
         const int sx = __shfl_sync(SSLAPB_FULL, br.x, src), sy = __shfl_sync(SSLAPB_FULL, br.y, src);
@@ -151,16 +157,12 @@ __device__ __forceinline__ SslapbBid row_bid_core(const int *__restrict__ cols, 
     }
     const double wi = skey ? sslapb_key2double(skey) : SSLAPB_NEG_INF;   // w_i = -inf for a single-entry row (:344)
     o.bid = (bc - wi) + eps;                                   // :360
+    if (pass || !(thr > SSLAPB_NEG_INF) || ((thr - pmin) < wi)) break;
+    thr = SSLAPB_NEG_INF;                                      // the skipped entries might matter: sweep again, gather all
+    }
     return o;
 }
 
-// Bound-pruned sweep of one row that fits a single warp pass (grid regime).  Exact, but most price gathers are skipped:
-//   v_k = a_k - p_k <= a_k - L for any lower bound L of the prices, so an entry whose bound a_k - L is strictly below the
-//   second-best value found among the gathered entries can be neither the best nor the second best.
-// Pass 1 gathers the entries within `spread` (current price range, a heuristic) of the row's largest a_k; the bound test
-// then either proves the rest irrelevant (usual case) or names the entries to gather in pass 2 (after which no further
-// violation is possible because the second-best value only grows).  The random price gathers are what limits the
-// sweep (one L1TEX wavefront and one 32-byte L2 sector per 8-byte price), not the 12 B/entry stream.
 struct SslapbStreamChunk { int4 cj; double2 va, vb; };
 __device__ __forceinline__ SslapbStreamChunk sslapb_stream_chunk(const int *__restrict__ cols,
                                                                  const double *__restrict__ vals, long long start,
@@ -202,13 +204,6 @@ __device__ __forceinline__ unsigned long long sslapb_key_of(double v)
     return (unsigned long long)(bits ^ ((bits >> 63) | (long long)0x8000000000000000ull));
 }
 
-__device__ __forceinline__ float sslapb_redux_max_f32(float v)
-{
-    float r;
-    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
-    return r;
-}
-
 // Cross-lane part shared by the single-pass sweeps: lexicographic maximum of (value, row index) and the second largest
 // value of the row, from each lane's (best, second, index) — five REDUX on the integer images of the values.
 struct SslapbRowTop { bool iswin; unsigned own; unsigned long long skey; };
@@ -235,52 +230,42 @@ __device__ __forceinline__ SslapbRowTop sslapb_row_top2(double b, double s, int 
 #define SSLAPB_KEY_NEG_INF 0x000fffffffffffffull
 
 // Bound-pruned sweep of one row that fits a single warp pass (grid regime).  Exact, but most price gathers are skipped:
-//   v_k = a_k - p_k <= a_k - L for any lower bound L of the prices, so an entry whose bound a_k - L is strictly below the
-//   second-best value found among the gathered entries can be neither the best nor the second best.
-// Pass 1 gathers the entries within `spread` (current price range — a heuristic, evaluated in float32) of the row's
-// largest a_k; the float64 bound test then either proves the rest irrelevant (usual case) or names the entries to gather
-// in pass 2 (after which no further violation is possible because the second-best value only grows).
-// Entries of the chunk that belong to neighbouring rows are replaced by a = -inf up front.
+//   v_k = a_k - p_k <= a_k - L for any lower bound L of the prices.  Only the entries with a_k >= thr are gathered, where
+//   thr = (static row maximum of a) - (price spread at the start of the phase) is a heuristic.  Every other entry has
+//   a_k < thr, hence fl(a_k - p_k) <= fl(a_k - L) <= fl(thr - L) (rounding is monotone), so ONE uniform comparison
+//   fl(thr - L) < (second-best value found) proves that none of them can be the best or the second best.  If it fails
+//   (rare: the spread is stale because prices moved inside the phase) the row is redone with every entry gathered.
+// The random price gathers, not the 12 B/entry stream, are what loads L1TEX/L2 in this kernel (one wavefront and one
+// 32-byte sector per 8-byte price).  Entries of the chunk that belong to neighbouring rows are replaced by a = -inf.
 __device__ __forceinline__ SslapbBid row_bid_pruned(const SslapbStreamChunk &C, const double *price, long long start,
-                                                    long long end, int lane, double eps, double pmin, float spread,
+                                                    long long end, int lane, double eps, double pmin, double thr,
                                                     int &second_pass)
 {
     const long long ch = (start >> 2) + lane;
     const int off = (int)((ch << 2) - start);                 // row index of slot 0 (may be negative)
     const int deg = (int)(end - start);
     const int4 cj = C.cj;
-    const bool m0 = (unsigned)off < (unsigned)deg, m1 = (unsigned)(off + 1) < (unsigned)deg;
-    const bool m2 = (unsigned)(off + 2) < (unsigned)deg, m3 = (unsigned)(off + 3) < (unsigned)deg;
-    const double a0 = m0 ? C.va.x : SSLAPB_NEG_INF, a1 = m1 ? C.va.y : SSLAPB_NEG_INF;
-    const double a2 = m2 ? C.vb.x : SSLAPB_NEG_INF, a3 = m3 ? C.vb.y : SSLAPB_NEG_INF;
-    // heuristic gather set (float32, rounded towards gathering more)
-    const float f0 = __double2float_ru(a0), f1 = __double2float_ru(a1), f2 = __double2float_ru(a2), f3 = __double2float_ru(a3);
-    const float fmx = sslapb_redux_max_f32(fmaxf(fmaxf(f0, f1), fmaxf(f2, f3)));
-    const float thr = fmx - spread - 1e-3f * fabsf(fmx);
-    bool g0 = f0 >= thr, g1 = f1 >= thr, g2 = f2 >= thr, g3 = f3 >= thr;   // -inf (absent) is never gathered
-    double v0 = SSLAPB_NEG_INF, v1 = SSLAPB_NEG_INF, v2 = SSLAPB_NEG_INF, v3 = SSLAPB_NEG_INF;
-    if (g0) v0 = a0 - price[cj.x];
-    if (g1) v1 = a1 - price[cj.y];
-    if (g2) v2 = a2 - price[cj.z];
-    if (g3) v3 = a3 - price[cj.w];
-    SslapbLaneTop lt = sslapb_lane_top2(v0, v1, v2, v3);
-    bool mw = (lt.w & 2) ? ((lt.w & 1) ? g3 : g2) : ((lt.w & 1) ? g1 : g0);
-    SslapbRowTop rt = sslapb_row_top2(lt.b, lt.s, (mw && (unsigned)(off + lt.w) < (unsigned)deg) ? off + lt.w : -1);
-    {
-        // exactness test for the entries not gathered: is a_k - L (>= v_k) still strictly below the second-best value?
+    const double a0 = (unsigned)off < (unsigned)deg ? C.va.x : SSLAPB_NEG_INF;
+    const double a1 = (unsigned)(off + 1) < (unsigned)deg ? C.va.y : SSLAPB_NEG_INF;
+    const double a2 = (unsigned)(off + 2) < (unsigned)deg ? C.vb.x : SSLAPB_NEG_INF;
+    const double a3 = (unsigned)(off + 3) < (unsigned)deg ? C.vb.y : SSLAPB_NEG_INF;
+    SslapbLaneTop lt;
+    SslapbRowTop rt;
+#pragma unroll 1
+    for (int pass = 0;; ++pass) {
+        double v0 = SSLAPB_NEG_INF, v1 = SSLAPB_NEG_INF, v2 = SSLAPB_NEG_INF, v3 = SSLAPB_NEG_INF;
+        if (a0 >= thr) v0 = a0 - price[cj.x];                  // thr > -inf on the first pass: absent slots never gathered;
+        if (a1 >= thr) v1 = a1 - price[cj.y];                  // second pass (thr = -inf): they give -inf - p = -inf
+        if (a2 >= thr) v2 = a2 - price[cj.z];
+        if (a3 >= thr) v3 = a3 - price[cj.w];
+        lt = sslapb_lane_top2(v0, v1, v2, v3);
+        const int bi = ((unsigned)(off + lt.w) < (unsigned)deg && lt.b > SSLAPB_NEG_INF) ? off + lt.w : -1;
+        rt = sslapb_row_top2(lt.b, lt.s, bi);
+        if (pass || !(thr > SSLAPB_NEG_INF)) break;            // nothing was skipped
         const double sval = rt.skey > SSLAPB_KEY_NEG_INF ? sslapb_key2double(rt.skey) : SSLAPB_NEG_INF;
-        const bool x0 = m0 && !g0 && !((a0 - pmin) < sval), x1 = m1 && !g1 && !((a1 - pmin) < sval);
-        const bool x2 = m2 && !g2 && !((a2 - pmin) < sval), x3 = m3 && !g3 && !((a3 - pmin) < sval);
-        if (__any_sync(SSLAPB_FULL, x0 | x1 | x2 | x3)) {
-            ++second_pass;
-            if (x0) { v0 = a0 - price[cj.x]; g0 = true; }
-            if (x1) { v1 = a1 - price[cj.y]; g1 = true; }
-            if (x2) { v2 = a2 - price[cj.z]; g2 = true; }
-            if (x3) { v3 = a3 - price[cj.w]; g3 = true; }
-            lt = sslapb_lane_top2(v0, v1, v2, v3);
-            mw = (lt.w & 2) ? ((lt.w & 1) ? g3 : g2) : ((lt.w & 1) ? g1 : g0);
-            rt = sslapb_row_top2(lt.b, lt.s, (mw && (unsigned)(off + lt.w) < (unsigned)deg) ? off + lt.w : -1);
-        }
+        if ((thr - pmin) < sval) break;                        // uniform: nothing that was skipped can matter
+        ++second_pass;
+        thr = SSLAPB_NEG_INF;
     }
     const int src = rt.own ? (__ffs(rt.own) - 1) : lane;
     const double myc = (lt.w & 2) ? ((lt.w & 1) ? a3 : a2) : ((lt.w & 1) ? a1 : a0);
@@ -288,7 +273,7 @@ __device__ __forceinline__ SslapbBid row_bid_pruned(const SslapbStreamChunk &C, 
     const double bc = __shfl_sync(SSLAPB_FULL, myc, src);
     const int bj = __shfl_sync(SSLAPB_FULL, myj, src);
     SslapbBid o;
-    o.j = rt.own ? bj : -1;
+    o.j = rt.own ? bj : -1;                                    // -1: every candidate at -inf -> the caller runs the generic sweep
     o.powner = -1; o.pdeg = 0; o.pstart = 0;
     const double wi = rt.skey > SSLAPB_KEY_NEG_INF ? sslapb_key2double(rt.skey) : SSLAPB_NEG_INF;   // :344
     o.bid = (bc - wi) + eps;                                   // :360
@@ -298,9 +283,9 @@ __device__ __forceinline__ SslapbBid row_bid_pruned(const SslapbStreamChunk &C, 
 template <int W>
 __device__ __forceinline__ void row_bid(const int *__restrict__ cols, const double *__restrict__ vals,
                                         const double *price, long long start, long long end, int t, double eps,
-                                        int &jbest, double &bid)
+                                        int &jbest, double &bid, double pmin = 0.0, double thr = -__builtin_huge_val())
 {
-    const SslapbBid o = row_bid_core<W, false>(cols, vals, price, nullptr, start, end, t, eps);
+    const SslapbBid o = row_bid_core<W, false>(cols, vals, price, nullptr, start, end, t, eps, pmin, thr);
     jbest = o.j;
     bid = o.bid;
 }
@@ -311,9 +296,9 @@ __device__ __forceinline__ void row_bid(const int *__restrict__ cols, const doub
 template <int W>
 __device__ __noinline__ SslapbBid row_bid_rec(const int *__restrict__ cols, const double *__restrict__ vals,
                                               const SslapbObjRec *rec, long long start, long long end, int t,
-                                              double eps)
+                                              double eps, double pmin = 0.0, double thr = -__builtin_huge_val())
 {
-    return row_bid_core<W, true>(cols, vals, nullptr, rec, start, end, t, eps);
+    return row_bid_core<W, true>(cols, vals, nullptr, rec, start, end, t, eps, pmin, thr);
 }
 
 // eCE / objective sweep of one row by a full warp (auction_.pyx:460-483 and :504-521).
@@ -581,7 +566,7 @@ __device__ __forceinline__ int chain_rounds(const SslapbAuctionParams &P, double
 // person — it lost — or the owner it evicted, whose row was requested during the sweep), publishes (object, bid), and
 // after one barrier decides by itself whether it won (no serial merge); winners commit; after a second barrier every
 // warp derives the compacted list (push_all_left, auction_.pyx:137-162) redundantly from shared memory.
-__device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double eps, int nu, int *s_list,
+__device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double eps, const double *s_bounds, int nu, int *s_list,
                                             long long *s_start, int *s_deg, int *s_j, double *s_bidv, long long &its,
                                             long long max_iter, int &done, long long &rounds, int &me, long long &st,
                                             int &dg)
@@ -605,8 +590,9 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
         if (active) {
             bool ok = single;
             if (ok) ok = sweep_single(P, cur, st, dg, eps, true, B, nxt, nsingle);
-            if (!ok) {                                         // long row, or every candidate at -inf: exact generic sweep
-                B = row_bid_rec<32>(P.cols, P.vals, P.rec, st, st + dg, lane, eps);
+            if (!ok) {                                         // long row (bound-pruned), or every candidate at -inf (exact, unpruned)
+                B = row_bid_rec<32>(P.cols, P.vals, P.rec, st, st + dg, lane, eps, s_bounds[0],
+                                    single ? SSLAPB_NEG_INF : __ldg(P.rowmax + me) - s_bounds[1]);
                 ok = B.j >= 0;
                 const long long n0 = B.pstart >> 2, n1 = (B.pstart + B.pdeg + 3) >> 2;
                 nsingle = (n1 - n0) <= 32;
@@ -676,11 +662,12 @@ struct SslapbPartial {
     int bi, bj;                   // its row index / column
     int4 br;                      // its object's record {start lo, start hi, owner, deg}
 };
-struct SslapbCoopRow { long long st; int me, dg, state; };   // state: 0 next row is long, 1 short, 2 frontier empty, 3 max_iter, 4 abort
+struct SslapbCoopRow { long long st; double thr; int me, dg, state; };   // state: 0 sweep this (long) row, 1 next row is short,
+                                                                        // 2 frontier empty, 3 max_iter, 4 abort
 
 __device__ __forceinline__ SslapbPartial row_partial_rec(const int *__restrict__ cols, const double *__restrict__ vals,
                                                          const SslapbObjRec *rec, long long start, long long end, int lane,
-                                                         int trip0, int tstride)
+                                                         int trip0, int tstride, double thr)
 {
     const int4 *c4 = reinterpret_cast<const int4 *>(cols);
     const double2 *v2 = reinterpret_cast<const double2 *>(vals);
@@ -697,7 +684,8 @@ __device__ __forceinline__ SslapbPartial row_partial_rec(const int *__restrict__
         const int4 cj = __ldg(c4 + ch);
         const double2 va = __ldg(v2 + 2 * ch), vb = __ldg(v2 + 2 * ch + 1);
         const int lo = (int)(start - (ch << 2)), hi = (int)min(end - (ch << 2), 4ll);
-        const bool m0 = (0 >= lo) & (0 < hi), m1 = (1 >= lo) & (1 < hi), m2 = (2 >= lo) & (2 < hi), m3 = (3 >= lo) & (3 < hi);
+        const bool m0 = (0 >= lo) & (0 < hi) & (va.x >= thr), m1 = (1 >= lo) & (1 < hi) & (va.y >= thr);   // bound pruning
+        const bool m2 = (2 >= lo) & (2 < hi) & (vb.x >= thr), m3 = (3 >= lo) & (3 < hi) & (vb.y >= thr);
         SslapbRec256 q0, q1, q2, q3;
         q0.start = q1.start = q2.start = q3.start = 0ull;
         q0.owner_deg = q1.owner_deg = q2.owner_deg = q3.owner_deg = 0xffffffffull;
@@ -754,9 +742,9 @@ __device__ __forceinline__ SslapbPartial row_partial_rec(const int *__restrict__
 }
 
 // executed by ALL warps of CTA 0 while the single bidder's row is long; warp 0 carries the list entry in (li, lst, ldg)
-__device__ __forceinline__ int coop_chain_rounds(const SslapbAuctionParams &P, double eps, SslapbPartial *s_part,
-                                                 SslapbCoopRow *s_row, int &li, long long &lst, int &ldg, long long &its,
-                                                 long long max_iter, int &done, long long &rounds)
+__device__ __forceinline__ int coop_chain_rounds(const SslapbAuctionParams &P, double eps, double pmin, double spread,
+                                                 SslapbPartial *s_part, SslapbCoopRow *s_row, int &li, long long &lst,
+                                                 int &ldg, long long &its, long long max_iter, int &done, long long &rounds)
 {
     const int lane = threadIdx.x & 31, warp = __shfl_sync(SSLAPB_FULL, (int)(threadIdx.x >> 5), 0);
     constexpr int NW = SSLAPB_THREADS / 32;
@@ -764,7 +752,8 @@ __device__ __forceinline__ int coop_chain_rounds(const SslapbAuctionParams &P, d
     for (;;) {
         const long long st = s_row->st;
         const int dg = s_row->dg;
-        const SslapbPartial part = row_partial_rec(P.cols, P.vals, P.rec, st, st + dg, lane, warp, NW);
+        const double thr = s_row->thr;
+        const SslapbPartial part = row_partial_rec(P.cols, P.vals, P.rec, st, st + dg, lane, warp, NW, thr);
         if (lane == 0) s_part[warp] = part;
         __syncthreads();
         if (warp == 0) {
@@ -783,8 +772,12 @@ __device__ __forceinline__ int coop_chain_rounds(const SslapbAuctionParams &P, d
             const unsigned slo = __reduce_max_sync(SSLAPB_FULL, chh == shi ? chl : 0u);
             const unsigned long long skey = ((unsigned long long)shi << 32) | slo;
             const unsigned own = __ballot_sync(SSLAPB_FULL, iswin);
+            const double wi0 = skey > SSLAPB_KEY_NEG_INF ? sslapb_key2double(skey) : SSLAPB_NEG_INF;
             int state;
-            if (own == 0u) { state = 4; done = 4; }            // empty row: rejected at CSR build, cannot happen
+            double nthr = SSLAPB_NEG_INF;
+            if (thr > SSLAPB_NEG_INF && !((thr - pmin) < wi0)) {
+                state = 0;                                     // the skipped entries might matter: same row again, gather all
+            } else if (own == 0u) { state = 4; done = 4; }     // empty row: rejected at CSR build, cannot happen
             else {
                 const int src = __ffs(own) - 1;
                 SslapbBid B;
@@ -803,10 +796,11 @@ __device__ __forceinline__ int coop_chain_rounds(const SslapbAuctionParams &P, d
                 else {
                     li = B.powner; lst = B.pstart; ldg = B.pdeg;
                     state = ((((lst + ldg + 3) >> 2) - (lst >> 2)) > 32) ? 0 : 1;
+                    if (state == 0) nthr = __ldg(P.rowmax + li) - spread;
                 }
                 if (its >= max_iter) { done = 3; state = 3; }
             }
-            if (lane == 0) { s_row->st = lst; s_row->dg = ldg; s_row->me = li; s_row->state = state; }
+            if (lane == 0) { s_row->st = lst; s_row->dg = ldg; s_row->me = li; s_row->state = state; s_row->thr = nthr; }
         }
         __syncthreads();
         if (s_row->state != 0) break;
@@ -817,7 +811,7 @@ __device__ __forceinline__ int coop_chain_rounds(const SslapbAuctionParams &P, d
 
 // CTA 0 finishes the eps-phase alone once nu <= t_small (nu only shrinks inside a phase).
 __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, SslapbCtrl *C, int nu, float eps_f,
-                                             long long its, long long max_iter)
+                                             long long its, long long max_iter, double pmin, double spread)
 {
     __shared__ int s_list[32], s_deg[32], s_j[32];
     __shared__ long long s_start[32];
@@ -827,6 +821,7 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
     __shared__ long long s_its, s_rw, s_rs;
     __shared__ SslapbPartial s_part[SSLAPB_THREADS / 32];
     __shared__ SslapbCoopRow s_row;
+    __shared__ double s_bounds[2];                             // {pmin, spread}: only the rare long-row paths read them
 
     // warp index through a shuffle: tells the compiler it is warp-uniform (same idiom as cutlass::canonical_warp_idx_sync)
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(SSLAPB_FULL, tid >> 5, 0);
@@ -834,6 +829,7 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
     int li = -1, ldg = 0, done = 0;
     long long lst = 0;
     long long rw = 0, rs = 0;
+    if (tid == 0) { s_bounds[0] = pmin; s_bounds[1] = spread; }
     if (warp == 0) {
         if (lane < nu) {
             const int v = P.list[lane];
@@ -850,7 +846,8 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
     while (nu > SSLAPB_THREADS / 32 && !done) {
         for (int a = warp; a < nu; a += SSLAPB_THREADS / 32) {
             const long long st = s_start[a];
-            const SslapbBid b = row_bid_rec<32>(P.cols, P.vals, P.rec, st, st + s_deg[a], lane, eps);
+            const SslapbBid b = row_bid_rec<32>(P.cols, P.vals, P.rec, st, st + s_deg[a], lane, eps, s_bounds[0],
+                                                __ldg(P.rowmax + s_list[a]) - s_bounds[1]);
             if (lane == 0) s_bid[a] = b;
         }
         __syncthreads();
@@ -868,7 +865,7 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
         its = __shfl_sync(SSLAPB_FULL, s_its, 0);
     }
     // ---- 2..16 bidders: one warp per list position, distributed merge
-    if (nu > 1 && !done) nu = multi_rounds(P, eps, nu, s_list, s_start, s_deg, s_j, s_bidv, its, max_iter, done, rw, li, lst, ldg);
+    if (nu > 1 && !done) nu = multi_rounds(P, eps, s_bounds, nu, s_list, s_start, s_deg, s_j, s_bidv, its, max_iter, done, rw, li, lst, ldg);
 
     unsigned long long tw1 = sslapb_globaltimer();
     // ---- single-bidder chain: warp 0 alone, no block barrier (after multi_rounds warp a holds position a in registers);
@@ -879,13 +876,14 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
             const bool longrow = nu == 1 && !done;             // chain_rounds stops in front of a long row
             if (lane == 0) {
                 s_row.st = lst; s_row.dg = ldg; s_row.me = li; s_row.state = longrow ? 0 : 1;
+                s_row.thr = longrow ? __ldg(P.rowmax + li) - s_bounds[1] : SSLAPB_NEG_INF;
                 s_nu = nu; s_done = done; s_its = its; s_rw = rw; s_rs = rs;
             }
         }
         __syncthreads();
         if (s_row.state != 0) break;
         __syncthreads();
-        const int cnu = coop_chain_rounds(P, eps, s_part, &s_row, li, lst, ldg, its, max_iter, done, rs);
+        const int cnu = coop_chain_rounds(P, eps, s_bounds[0], s_bounds[1], s_part, &s_row, li, lst, ldg, its, max_iter, done, rs);
         if (warp == 0) nu = cnu;
         __syncthreads();
     }
@@ -973,7 +971,8 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
         // price bounds for the pruned sweep, taken at the start of the eps-phase: pmin stays a valid lower bound all phase
         // long (prices never decrease); the spread is only a heuristic for which candidates to gather first
         const double pmin = sslapb_key2double(phase_slot ? s_top.pmin1 : s_top.pmin0);
-        const float spread = __double2float_ru(sslapb_key2double(s_top.pmax) - pmin) + 2.0f * eps_f;
+        double spread = (sslapb_key2double(s_top.pmax) - pmin) + 2.0 * (double)eps_f;
+        if (!(spread < 1.7e308)) spread = __longlong_as_double(0x7ff0000000000000ll);   // inf / NaN (infinite prices): no pruning
         __syncthreads();                                       // s_top is rewritten only after every thread has read it
         if (done) break;
 
@@ -1005,12 +1004,12 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
                 int j; double bid;
                 if ((((en + 3) >> 2) - (st >> 2)) <= 32) {
                     const SslapbStreamChunk c = sslapb_stream_chunk(P.cols, P.vals, st, en, lane);
-                    const SslapbBid o = row_bid_pruned(c, P.price, st, en, lane, eps, pmin, spread, n2nd);
+                    const SslapbBid o = row_bid_pruned(c, P.price, st, en, lane, eps, pmin, __ldg(P.rowmax + v) - spread, n2nd);
                     j = o.j; bid = o.bid;
                     // every candidate at -inf (objects priced +inf by single-choice bidders): the exact generic sweep decides
                     if (j < 0) row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);
-                } else {
-                    row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);
+                } else {                                       // long row: multi-trip sweep, same bound pruning
+                    row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid, pmin, __ldg(P.rowmax + v) - spread);
                 }
                 emit_bid(a, j, bid);
             }
@@ -1122,7 +1121,7 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
             }
         } else {
             // ================================ warp-list regimes: CTA 0 finishes the phase ================================
-            if (blockIdx.x == 0) small_regime(P, C, nu, eps_f, its, max_iter);
+            if (blockIdx.x == 0) small_regime(P, C, nu, eps_f, its, max_iter, pmin, spread);
             GB();
         }
 
@@ -1168,7 +1167,8 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
                 const unsigned xh = __reduce_max_sync(SSLAPB_FULL, (unsigned)(kmax >> 32));
                 if (lane == 0) {
                     atomicMin(&C->pmin_key[phase_slot ^ 1], ((unsigned long long)mh << 32) | ml);
-                    atomicMax(&C->pmax_key, ((unsigned long long)xh << 32) | 0xffffffffull);   // rounded up: heuristic only
+                    const unsigned long long kx = ((unsigned long long)xh << 32) | 0xffffffffull;   // rounded up: heuristic only
+                    atomicMax(&C->pmax_key, kx > 0xfff0000000000000ull ? 0xfff0000000000000ull : kx);   // never beyond +inf
                 }
             }
             GB();
@@ -1228,7 +1228,8 @@ __global__ void __launch_bounds__(1024, 1) sslapb_bid_sweep_kernel(SslapbAuction
     const double eps = (double)eps_f;
     const bool prune = (merge & 2) == 0;                       // bit 1 of `merge` switches the bound pruning off (A/B measurement)
     const double pmin = sslapb_key2double(P.ctrl->pmin_key[0]);
-    const float spread = __double2float_ru(sslapb_key2double(P.ctrl->pmax_key) - pmin);
+    double spread = sslapb_key2double(P.ctrl->pmax_key) - pmin;
+    if (!(spread < 1.7e308)) spread = __longlong_as_double(0x7ff0000000000000ll);
     int n2nd = 0;
     merge &= 1;
     // plain loop at full occupancy: the kernel is instruction-issue bound, a software pipeline across rows buys nothing
@@ -1236,13 +1237,13 @@ __global__ void __launch_bounds__(1024, 1) sslapb_bid_sweep_kernel(SslapbAuction
         const int i = bidders ? bidders[a] : a;
         const long long st = __ldg(P.rowptr + i), en = __ldg(P.rowptr + i + 1);
         int j; double bid;
-        if (prune && (((en + 3) >> 2) - (st >> 2)) <= 32) {
+        if ((((en + 3) >> 2) - (st >> 2)) <= 32) {
             const SslapbStreamChunk c = sslapb_stream_chunk(P.cols, P.vals, st, en, lane);
-            const SslapbBid o = row_bid_pruned(c, P.price, st, en, lane, eps, pmin, spread, n2nd);
+            const SslapbBid o = row_bid_pruned(c, P.price, st, en, lane, eps, pmin, prune ? __ldg(P.rowmax + i) - spread : SSLAPB_NEG_INF, n2nd);
             j = o.j; bid = o.bid;
             if (j < 0) row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);   // all candidates at -inf
         } else {
-            row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);
+            row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid, pmin, prune ? __ldg(P.rowmax + i) - spread : SSLAPB_NEG_INF);
         }
         if (lane == 0) {
             P.bidj[a] = j;
@@ -1391,7 +1392,7 @@ __global__ void __launch_bounds__(128) sslapb_auction_batch_kernel(SslapbBatchPa
             int j; double bid;
             if ((((en + 3) >> 2) - (st >> 2)) <= 32) {
                 const SslapbStreamChunk c = sslapb_stream_chunk(B.cols, B.vals, st, en, lane);
-                const SslapbBid o = row_bid_pruned(c, B.price, st, en, lane, epsd, 0.0, __int_as_float(0x7f800000), dummy2nd);
+                const SslapbBid o = row_bid_pruned(c, B.price, st, en, lane, epsd, 0.0, SSLAPB_NEG_INF, dummy2nd);
                 j = o.j; bid = o.bid;
                 if (j < 0) row_bid<32>(B.cols, B.vals, B.price, st, en, lane, epsd, j, bid);   // all candidates at -inf
             } else {

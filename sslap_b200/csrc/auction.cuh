@@ -45,6 +45,8 @@ struct SslapbAuctionParams {
     const long long *rowptr;  // N+1 row start offsets (i_starts_stops, auction_.pyx:223)
     const int *cols;          // flat_j (:229); 16-byte aligned base, >= 4 entries of slack after nnz
     const double *vals;       // sign-folded values ('min' negated, :236-237); same alignment/slack
+    const double *rowmax;     // per person: max_j a_ij (static; the pruned sweeps gather only entries within the price
+                              // spread of it)
     double *price;            // p (:220)
     SslapbObjRec *rec;        // per-object record incl. object_to_person (:232)
     int *p2o;                 // person_to_object (:231)

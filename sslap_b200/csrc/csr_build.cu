@@ -177,6 +177,29 @@ extern "C" cudaError_t sslapb_launch_index_max(const void *rows, const void *col
     return cudaGetLastError();
 }
 
+// per-row maximum of the (sign-folded) values: warp per row
+__global__ void __launch_bounds__(256) sslapb_rowmax_kernel(const long long *__restrict__ rowptr,
+                                                            const double *__restrict__ vals, long long nrows,
+                                                            double *__restrict__ rowmax)
+{
+    const int lane = threadIdx.x & 31;
+    const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = gwarp; r < nrows; r += nwarps) {
+        double m = SSLAPB_NEG_INF;
+        for (long long e = rowptr[r] + lane; e < rowptr[r + 1]; e += 32) m = fmax(m, vals[e]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(SSLAPB_FULL, m, off));
+        if (lane == 0) rowmax[r] = m;
+    }
+}
+
+extern "C" cudaError_t sslapb_launch_rowmax(const long long *rowptr, const double *vals, long long nrows, double *rowmax,
+                                            int sms, cudaStream_t stream)
+{
+    sslapb_rowmax_kernel<<<sms * 8, 256, 0, stream>>>(rowptr, vals, nrows, rowmax);
+    return cudaGetLastError();
+}
+
 extern "C" cudaError_t sslapb_launch_coo_ingest(const void *rows, const void *cols, int idx_bytes, long long stride,
                                                 const double *val, long long nnz, int N, int M, int negate,
                                                 int *cols32, double *vals, long long *rowptr, SslapbBuildFlags *F,
