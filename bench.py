@@ -237,7 +237,7 @@ def main():
                           "sections_ms": [round(float(x), 3) for x in meta.prof_ms]},
             "e2e": {"value": total_nnz / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(loc.nbytes + val.nbytes), "d2h_bytes_per_step": int(sol.nbytes + 8 * N_ROWS + 256)},
-            "gpu_launches": 3 * args.steps,          # per step: coo_ingest, auction_init, persistent auction kernel
+            "gpu_launches": 4 * args.steps,          # per step: coo_ingest, rowmax, auction_init, persistent auction kernel
             "roofline": {"kernel": "sslapb_bid_sweep_kernel (full frontier, N bidders, merge atomics on)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "bytes_per_launch": sweep_bytes, "avg_launch_us": avg.value * 1e3,

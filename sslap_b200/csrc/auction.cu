@@ -249,34 +249,28 @@ __device__ __forceinline__ SslapbBid row_bid_pruned(const SslapbStreamChunk &C, 
     const double a1 = (unsigned)(off + 1) < (unsigned)deg ? C.va.y : SSLAPB_NEG_INF;
     const double a2 = (unsigned)(off + 2) < (unsigned)deg ? C.vb.x : SSLAPB_NEG_INF;
     const double a3 = (unsigned)(off + 3) < (unsigned)deg ? C.vb.y : SSLAPB_NEG_INF;
-    SslapbLaneTop lt;
-    SslapbRowTop rt;
-#pragma unroll 1
-    for (int pass = 0;; ++pass) {
-        double v0 = SSLAPB_NEG_INF, v1 = SSLAPB_NEG_INF, v2 = SSLAPB_NEG_INF, v3 = SSLAPB_NEG_INF;
-        if (a0 >= thr) v0 = a0 - price[cj.x];                  // thr > -inf on the first pass: absent slots never gathered;
-        if (a1 >= thr) v1 = a1 - price[cj.y];                  // second pass (thr = -inf): they give -inf - p = -inf
-        if (a2 >= thr) v2 = a2 - price[cj.z];
-        if (a3 >= thr) v3 = a3 - price[cj.w];
-        lt = sslapb_lane_top2(v0, v1, v2, v3);
-        const int bi = ((unsigned)(off + lt.w) < (unsigned)deg && lt.b > SSLAPB_NEG_INF) ? off + lt.w : -1;
-        rt = sslapb_row_top2(lt.b, lt.s, bi);
-        if (pass || !(thr > SSLAPB_NEG_INF)) break;            // nothing was skipped
-        const double sval = rt.skey > SSLAPB_KEY_NEG_INF ? sslapb_key2double(rt.skey) : SSLAPB_NEG_INF;
-        if ((thr - pmin) < sval) break;                        // uniform: nothing that was skipped can matter
-        ++second_pass;
-        thr = SSLAPB_NEG_INF;
-    }
+    double v0 = SSLAPB_NEG_INF, v1 = SSLAPB_NEG_INF, v2 = SSLAPB_NEG_INF, v3 = SSLAPB_NEG_INF;
+    if (a0 >= thr) v0 = a0 - price[cj.x];                      // thr > -inf: absent slots are never gathered;
+    if (a1 >= thr) v1 = a1 - price[cj.y];                      // thr = -inf (no pruning): they give -inf - p = -inf
+    if (a2 >= thr) v2 = a2 - price[cj.z];
+    if (a3 >= thr) v3 = a3 - price[cj.w];
+    const SslapbLaneTop lt = sslapb_lane_top2(v0, v1, v2, v3);
+    const int bi = ((unsigned)(off + lt.w) < (unsigned)deg && lt.b > SSLAPB_NEG_INF) ? off + lt.w : -1;
+    const SslapbRowTop rt = sslapb_row_top2(lt.b, lt.s, bi);
     const int src = rt.own ? (__ffs(rt.own) - 1) : lane;
     const double myc = (lt.w & 2) ? ((lt.w & 1) ? a3 : a2) : ((lt.w & 1) ? a1 : a0);
     const int myj = (lt.w & 2) ? ((lt.w & 1) ? cj.w : cj.z) : ((lt.w & 1) ? cj.y : cj.x);
     const double bc = __shfl_sync(SSLAPB_FULL, myc, src);
     const int bj = __shfl_sync(SSLAPB_FULL, myj, src);
-    SslapbBid o;
-    o.j = rt.own ? bj : -1;                                    // -1: every candidate at -inf -> the caller runs the generic sweep
-    o.powner = -1; o.pdeg = 0; o.pstart = 0;
     const double wi = rt.skey > SSLAPB_KEY_NEG_INF ? sslapb_key2double(rt.skey) : SSLAPB_NEG_INF;   // :344
+    SslapbBid o;
+    o.powner = -1; o.pdeg = 0; o.pstart = 0;
     o.bid = (bc - wi) + eps;                                   // :360
+    // j = -1 sends the caller to the exact generic sweep: every candidate at -inf, or (uniform test) a skipped entry
+    // might matter — rare: the spread is stale because prices moved inside the phase
+    const bool proven = !(thr > SSLAPB_NEG_INF) || ((thr - pmin) < wi);
+    if (!proven) ++second_pass;
+    o.j = (rt.own && proven) ? bj : -1;
     return o;
 }
 
@@ -478,7 +472,9 @@ __device__ __forceinline__ bool sweep_single(const SslapbAuctionParams &P, const
     const double v2 = m2 ? cur.vb.x - __longlong_as_double((long long)q2.price_bits) : SSLAPB_NEG_INF;
     const double v3 = m3 ? cur.vb.y - __longlong_as_double((long long)q3.price_bits) : SSLAPB_NEG_INF;
     const SslapbLaneTop lt = sslapb_lane_top2(v0, v1, v2, v3);
-    const int bi = ((unsigned)(off + lt.w) < (unsigned)dg) ? off + lt.w : -1;
+    // a lane whose best value is -inf reports nothing: real -inf candidates (objects priced +inf) cannot be told from the
+    // absent slots here, so rows whose candidates are ALL at -inf are left to the exact generic sweep (caller)
+    const int bi = ((unsigned)(off + lt.w) < (unsigned)dg && lt.b > SSLAPB_NEG_INF) ? off + lt.w : -1;
     const unsigned long long qs = (lt.w & 2) ? ((lt.w & 1) ? q3.start : q2.start) : ((lt.w & 1) ? q1.start : q0.start);
     const unsigned long long qo = (lt.w & 2) ? ((lt.w & 1) ? q3.owner_deg : q2.owner_deg) : ((lt.w & 1) ? q1.owner_deg : q0.owner_deg);
     // top-1 across the warp -> whose object -> request the owner's row right away
@@ -1232,24 +1228,39 @@ __global__ void __launch_bounds__(1024, 1) sslapb_bid_sweep_kernel(SslapbAuction
     if (!(spread < 1.7e308)) spread = __longlong_as_double(0x7ff0000000000000ll);
     int n2nd = 0;
     merge &= 1;
-    // plain loop at full occupancy: the kernel is instruction-issue bound, a software pipeline across rows buys nothing
-    for (int a = gwarp; a < nb; a += nwarps) {
-        const int i = bidders ? bidders[a] : a;
-        const long long st = __ldg(P.rowptr + i), en = __ldg(P.rowptr + i + 1);
+    // one row per warp at a time; the NEXT row's offsets and row maximum are requested one iteration ahead (one of the
+    // three dependent round trips per row: offsets -> entries -> prices)
+    int a = gwarp;
+    if (a >= nb) return;
+    int i = bidders ? bidders[a] : a;
+    long long st = __ldg(P.rowptr + i), en = __ldg(P.rowptr + i + 1);
+    double rmax = __ldg(P.rowmax + i);
+    for (;;) {
+        const int an = a + nwarps;
+        int in = 0;
+        long long stn = 0, enn = 0;
+        double rmaxn = 0.0;
+        if (an < nb) {
+            in = bidders ? bidders[an] : an;
+            stn = __ldg(P.rowptr + in); enn = __ldg(P.rowptr + in + 1);
+            rmaxn = __ldg(P.rowmax + in);
+        }
         int j; double bid;
         if ((((en + 3) >> 2) - (st >> 2)) <= 32) {
             const SslapbStreamChunk c = sslapb_stream_chunk(P.cols, P.vals, st, en, lane);
-            const SslapbBid o = row_bid_pruned(c, P.price, st, en, lane, eps, pmin, prune ? __ldg(P.rowmax + i) - spread : SSLAPB_NEG_INF, n2nd);
+            const SslapbBid o = row_bid_pruned(c, P.price, st, en, lane, eps, pmin, prune ? rmax - spread : SSLAPB_NEG_INF, n2nd);
             j = o.j; bid = o.bid;
-            if (j < 0) row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);   // all candidates at -inf
+            if (j < 0) row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);   // all candidates at -inf / unproven
         } else {
-            row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid, pmin, prune ? __ldg(P.rowmax + i) - spread : SSLAPB_NEG_INF);
+            row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid, pmin, prune ? rmax - spread : SSLAPB_NEG_INF);
         }
         if (lane == 0) {
             P.bidj[a] = j;
             P.bidv[a] = bid;
             if (merge && j >= 0) atomicMax(P.bidkey + j, sslapb_ord64(bid));
         }
+        if (an >= nb) break;
+        a = an; st = stn; en = enn; rmax = rmaxn;
     }
     if (n2nd && lane == 0) atomicAdd((unsigned long long *)&P.ctrl->prune_second_pass, (unsigned long long)n2nd);
 }

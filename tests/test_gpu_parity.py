@@ -332,3 +332,39 @@ def test_long_rows_take_the_generic_sweep(gpu, oracle_mod):
             h.set_option("t_small", 32)
         assert np.array_equal(got["sol"], want["sol"])
         assert_meta_equal(got["meta"], want["meta"])
+
+
+def test_randomized_differential_against_the_oracle(gpu, oracle_mod):
+    """120 seeded random instances across shapes, densities, cost kinds, objectives, eps options, iteration caps and
+    regime splits: `sol` and the integer meta keys must equal the oracle's bit for bit; so must the float64 prices."""
+    sslap_b200, nat, h = gpu
+    rng = np.random.default_rng(2024)
+    checked = 0
+    for case in range(120):
+        n = int(rng.integers(2, 400))
+        m = n + int(rng.integers(0, 30)) if rng.random() < 0.3 else n
+        density = float(rng.choice([0.02, 0.05, 0.1, 0.3, 0.7, 1.0]))
+        mode = "int" if rng.random() < 0.5 else "float"
+        loc, val = make_problem(n, density, mode, seed=1000 + case, m=m)
+        if rng.random() < 0.2:
+            val = np.round(val / 10.0)                      # heavy ties, zeros included
+        problem = "min" if rng.random() < 0.5 else "max"
+        kw = {}
+        r = rng.random()
+        if r < 0.15:
+            kw["eps_start"] = float(rng.choice([0.5, 3.0, 40.0]))
+        elif r < 0.25:
+            kw["max_iter"] = int(rng.integers(1, 200))
+        t_small = int(rng.choice([32, 32, 16, 4, 1, 0]))
+        h.set_option("t_small", t_small)
+        try:
+            g = sslap_b200.auction_solve(loc=loc if case % 2 else loc.astype(np.int64), val=val, size=(n, m),
+                                         problem=problem, cardinality_check=bool(case % 3), **kw)
+        finally:
+            h.set_option("t_small", 32)
+        o = oracle_mod.auction_solve(loc=loc, val=val, problem=problem, return_prices=True, **kw)
+        assert np.array_equal(g["sol"], o["sol"]), (case, n, m, density, mode, problem, kw, t_small)
+        assert_meta_equal(g["meta"], o["meta"])
+        assert np.array_equal(prices_of(nat, h, m), o["prices"]), (case, "prices")
+        checked += 1
+    assert checked == 120
