@@ -368,3 +368,41 @@ def test_randomized_differential_against_the_oracle(gpu, oracle_mod):
         assert np.array_equal(prices_of(nat, h, m), o["prices"]), (case, "prices")
         checked += 1
     assert checked == 120
+
+
+def test_randomized_dense_batch_and_hopcroft(gpu, oracle_mod):
+    """Seeded random instances through the other entry points: dense `mat` input (device dense -> CSR build), the batch
+    call, and Hopcroft-Karp on random (mostly deficient) graphs."""
+    sslap_b200, nat, h = gpu
+    rng = np.random.default_rng(77)
+    # dense matrices with -1 holes, rectangular allowed
+    for case in range(30):
+        n = int(rng.integers(2, 150)); m = n + int(rng.integers(0, 20))
+        mat = rng.integers(0, 50, (n, m)).astype(np.float64) if case % 2 else rng.uniform(0, 100, (n, m))
+        mat[rng.random((n, m)) < float(rng.choice([0.0, 0.3, 0.8]))] = -1
+        mat[np.arange(n), rng.permutation(m)[:n]] = rng.integers(0, 50, n)      # keep it feasible
+        problem = "min" if case % 3 else "max"
+        g = sslap_b200.auction_solve(mat=mat, problem=problem)
+        o = oracle_mod.auction_solve(mat=mat, problem=problem)
+        assert np.array_equal(g["sol"], o["sol"]), ("dense", case)
+        assert_meta_equal(g["meta"], o["meta"])
+    # one batch of 60 heterogeneous problems
+    probs, want = [], []
+    for k in range(60):
+        n = int(rng.integers(2, 200)); m = n + int(rng.integers(0, 10))
+        loc, val = make_problem(n, float(rng.choice([0.05, 0.2, 0.6])), "int" if k % 2 else "float", seed=500 + k, m=m)
+        probs.append((loc, val, (n, m)))
+        want.append(oracle_mod.auction_solve(loc=loc, val=val, problem="min"))
+    got = sslap_b200.auction_solve_batch(probs, problem="min")
+    for k, (g, w) in enumerate(zip(got, want)):
+        assert np.array_equal(g["sol"], w["sol"]), ("batch", k)
+        assert_meta_equal(g["meta"], w["meta"])
+    # Hopcroft-Karp on random graphs
+    for case in range(40):
+        n = int(rng.integers(1, 3000)); m = int(rng.integers(1, 3000)); e = int(rng.integers(1, 4 * max(n, m)))
+        key = np.unique(rng.integers(0, n, e).astype(np.int64) * m + rng.integers(0, m, e))
+        loc = np.stack([key // m, key % m], -1).astype(np.int32 if case % 2 else np.int64)
+        g = sslap_b200.hopcroft_solve(loc=loc)
+        o = oracle_mod.hopcroft_solve(loc=loc)
+        assert g["size"] == o["size"], ("hk", case)
+        assert_valid_matching(g, loc)
