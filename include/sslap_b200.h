@@ -131,7 +131,8 @@ int sslapb_get_prices(sslapb_handle *h, double *prices_out);
  * (bid_and_assign's bidding loop, auction_.pyx:339-365) over the CSR of the most recent problem on this handle.
  *   prices (n_cols, host, NULL = keep the handle's current prices), bidders (nb int32, host, NULL = persons 0..nb-1)
  *   merge bit 0: also perform the per-object atomicMax of the bids (:375-385); bit 1: disable the bound pruning of
- *   the price gathers (A/B measurement);  iters >= 1 timed launches, with an L2
+ *   the price gathers (A/B measurement); bit 2 (only with bidders == NULL, nb == n_rows): the streamed TMA-ring variant
+   of the sweep instead of the per-row kernel (same results);  iters >= 1 timed launches, with an L2
  *   flush (a write larger than L2) before each when flush_l2 != 0.
  *   jbest_out / bid_out (nb, host, may be NULL); *avg_ms_out = mean device time of one launch (CUDA events).
  */

@@ -27,6 +27,8 @@ cudaError_t sslapb_launch_dense_fill(const double *, int, int, int, const long l
 cudaError_t sslapb_launch_auction(const SslapbAuctionParams *, int, cudaStream_t);
 cudaError_t sslapb_auction_grid_size(int, int *);
 cudaError_t sslapb_launch_bid_sweep(const SslapbAuctionParams *, const int *, int, float, int, int, cudaStream_t);
+cudaError_t sslapb_launch_sweep_plan(const SslapbAuctionParams *, int, int *, cudaStream_t);
+cudaError_t sslapb_launch_bid_sweep_tma(const SslapbAuctionParams *, const int *, float, int, int, cudaStream_t);
 cudaError_t sslapb_launch_price_bounds(const SslapbAuctionParams *, cudaStream_t);
 cudaError_t sslapb_hk_launch_greedy(const long long *, const int *, int, int *, int *, SslapbHkFlags *, int, cudaStream_t);
 cudaError_t sslapb_hk_launch_phase_init(int, int, const int *, int *, int *, int *, int *, SslapbHkFlags *, int, cudaStream_t);
@@ -96,7 +98,7 @@ struct sslapb_handle {
     DevBuf sort_keys, sort_idx, sort_hist, sort_rows, sort_cols, sort_val;   // only for unsorted input
     DevBuf b_off, b_rows, b_cols, b_eps, b_meta, b_bad;                      // batched problems
     // auction state
-    DevBuf price, owner, p2o, list, mover, bidj, bidv, bidkey, winpos, hole_count, chosen, ctrl, bidders, flush;
+    DevBuf price, owner, p2o, list, mover, bidj, bidv, bidkey, winpos, hole_count, chosen, ctrl, bidders, flush, sweep_plan;
     // HK state
     DevBuf pair_u, pair_v, dist, visited, cursor, pred, hkflags;
 };
@@ -145,7 +147,7 @@ extern "C" void sslapb_destroy(sslapb_handle *h)
     cudaStreamSynchronize(h->stream);
     DevBuf *all[] = {&h->b_off, &h->b_rows, &h->b_cols, &h->b_eps, &h->b_meta, &h->b_bad, &h->sort_keys, &h->sort_idx, &h->sort_hist, &h->sort_rows, &h->sort_cols, &h->sort_val, &h->stage_idx, &h->stage_val, &h->stage_mat, &h->cols, &h->vals, &h->rowptr, &h->rowmax, &h->flags, &h->price,
                      &h->owner, &h->p2o, &h->list, &h->mover, &h->bidj, &h->bidv, &h->bidkey, &h->winpos,
-                     &h->hole_count, &h->chosen, &h->ctrl, &h->bidders, &h->flush, &h->pair_u, &h->pair_v, &h->dist,
+                     &h->hole_count, &h->chosen, &h->ctrl, &h->bidders, &h->flush, &h->sweep_plan, &h->pair_u, &h->pair_v, &h->dist,
                      &h->visited, &h->cursor, &h->pred, &h->hkflags};
     for (DevBuf *b : all) b->release();
     for (auto &ev : h->ev) cudaEventDestroy(ev);
@@ -566,6 +568,14 @@ extern "C" int sslapb_bid_sweep(sslapb_handle *h, const double *prices, const in
         if ((size_t)nb > (size_t)h->N) { CK(h->bidj.reserve((size_t)nb * 4)); CK(h->bidv.reserve((size_t)nb * 8)); P.bidj = h->bidj.as<int>(); P.bidv = h->bidv.as<double>(); }
     }
     CK(sslapb_launch_price_bounds(&P, h->stream));
+    // bit 2 of `merge`: identity frontier through the streamed (TMA ring) sweep, sweep_tma.cu — bit-identical results,
+    // measured slower than the per-row kernel on B200, kept for A/B runs
+    const bool streamed = !d_bidders && nb == h->N && (merge & 4);
+    merge &= 3;
+    if (streamed) {
+        CK(h->sweep_plan.reserve(((size_t)h->grid + 2) * 4));
+        CK(sslapb_launch_sweep_plan(&P, h->grid, h->sweep_plan.as<int>(), h->stream));
+    }
     const size_t flush_bytes = (size_t)256 << 20;
     if (flush_l2) CK(h->flush.reserve(flush_bytes));
     float total = 0.f;
@@ -573,7 +583,8 @@ extern "C" int sslapb_bid_sweep(sslapb_handle *h, const double *prices, const in
         if (merge) CK(cudaMemsetAsync(P.bidkey, 0, (size_t)h->M * 8, h->stream));
         if (flush_l2) CK(cudaMemsetAsync(h->flush.p, it & 0xff, flush_bytes, h->stream));
         CK(cudaEventRecord(h->ev[3], h->stream));
-        CK(sslapb_launch_bid_sweep(&P, d_bidders, nb, eps, merge, h->grid, h->stream));
+        if (streamed) CK(sslapb_launch_bid_sweep_tma(&P, h->sweep_plan.as<int>(), eps, merge, h->grid, h->stream));
+        else CK(sslapb_launch_bid_sweep(&P, d_bidders, nb, eps, merge, h->grid, h->stream));
         CK(cudaEventRecord(h->ev[4], h->stream));
         CK(cudaStreamSynchronize(h->stream));
         float ms = 0.f;

@@ -108,6 +108,38 @@ def test_bid_sweep_kernel_bit_exact(gpu, oracle_mod):
         assert np.array_equal(jb, oj) and np.array_equal(bd, ob)
 
 
+def test_bid_sweep_streamed_bit_exact(gpu, oracle_mod):
+    """Full-frontier sweep through the TMA-ring kernel (merge bit 2) and through the per-row kernel: both bit-exact
+    against the oracle, with and without bound pruning, incl. long rows, a rectangular problem and +inf prices."""
+    sslap_b200, nat, h = gpu
+    L = nat.load()
+    cases = [(1000, 0.01, "int", 3, None), (3000, 0.4, "float", 6, None), (20000, 0.0002, "float", 7, None),
+             (5000, 0.01, "float", 8, 7000), (64, 1.0, "float", 9, None)]
+    for (n, d, mode, seed, m) in cases:
+        loc, val = make_problem(n, d, mode, seed=seed, m=m)
+        M = m or n
+        sslap_b200.auction_solve(loc=loc, val=val, size=(n, M), cardinality_check=False, max_iter=1)
+        rng = np.random.default_rng(seed)
+        rowptr = np.searchsorted(loc[:, 0], np.arange(n + 1)).astype(np.int64)
+        for kind in range(3):
+            if kind == 0:
+                prices = rng.integers(0, 40, M).astype(np.float64) if mode == "int" else rng.uniform(0, 50, M)
+            elif kind == 1:
+                prices = np.zeros(M)
+            else:
+                prices = rng.uniform(0, 5, M)
+                prices[rng.integers(0, M, max(1, M // 50))] = np.inf
+            oj, ob = oracle_mod.bid_sweep(rowptr, loc[:, 1], -val, prices, np.arange(n, dtype=np.int32), 0.37)
+            for merge in (0, 2, 4, 6):
+                jb = np.empty(n, dtype=np.int32)
+                bd = np.empty(n, dtype=np.float64)
+                ms = C.c_float(0)
+                rc = L.sslapb_bid_sweep(h.ptr, prices.ctypes.data, None, n, 0.37, merge, 1, 0, jb.ctypes.data,
+                                        bd.ctypes.data, C.byref(ms))
+                assert rc == 0, h.last_error()
+                assert np.array_equal(jb, oj) and np.array_equal(bd, ob), (n, d, mode, kind, merge)
+
+
 @pytest.mark.parametrize("name", hopcroft_golden_names())
 def test_hopcroft_cardinality_bit_exact(gpu, name):
     sslap_b200, nat, h = gpu

@@ -10,7 +10,7 @@ n = 100000
 loc, val = make_problem(n, 0.001, "float", seed=0)
 sslap_b200.auction_solve(loc=loc, val=val, size=(n, n), cardinality_check=False)
 by = lambda nb: 12 * val.size * nb / n + 36 * nb
-for (nb, merge, flush) in [(n, 1, 1), (n, 5, 1), (n, 0, 1), (n, 3, 1), (n // 2, 1, 1), (n // 4, 1, 1), (n, 1, 0)]:
+for (nb, merge, flush) in [(n, 1, 1), (n, 0, 1), (n, 3, 1), (n // 2, 1, 1), (n // 4, 1, 1), (n, 1, 0)]:
     ms = C.c_float(0)
     rc = L.sslapb_bid_sweep(h.ptr, None, None, nb, 1e-5, merge, 10, flush, None, None, C.byref(ms))
     print(f"nb={nb} merge={merge} flush={flush}: {ms.value*1e3:.1f} us  {by(nb)/ms.value/1e6:.0f} GB/s", flush=True)
