@@ -19,12 +19,13 @@ cudaError_t sslapb_launch_coo_ingest(const void *, const void *, int, long long,
                                      int *, double *, long long *, SslapbBuildFlags *, int, cudaStream_t);
 cudaError_t sslapb_launch_coo_sort(const void *, const void *, int, long long, const double *, long long, int, unsigned *,
                                    unsigned *, unsigned *, unsigned *, long long *, int *, int *, double *, int, cudaStream_t);
-cudaError_t sslapb_launch_rowmax(const long long *, const double *, long long, double *, int, cudaStream_t);
+cudaError_t sslapb_launch_rowmax(const long long *, const double *, long long, double *, int *, int, cudaStream_t);
 cudaError_t sslapb_launch_index_max(const void *, const void *, int, long long, long long, long long *, int, cudaStream_t);
 cudaError_t sslapb_launch_dense_count(const double *, int, int, long long *, SslapbBuildFlags *, int, cudaStream_t);
 cudaError_t sslapb_launch_dense_fill(const double *, int, int, int, const long long *, int *, double *,
                                      SslapbBuildFlags *, int, cudaStream_t);
-cudaError_t sslapb_launch_auction(const SslapbAuctionParams *, int, cudaStream_t);
+cudaError_t sslapb_launch_auction(const SslapbAuctionParams *, int, int, cudaStream_t);
+int sslapb_coop_row_entries();
 cudaError_t sslapb_auction_grid_size(int, int *);
 cudaError_t sslapb_launch_bid_sweep(const SslapbAuctionParams *, const int *, int, float, int, int, cudaStream_t);
 cudaError_t sslapb_launch_sweep_plan(const SslapbAuctionParams *, int, int *, cudaStream_t);
@@ -92,6 +93,7 @@ struct sslapb_handle {
     long long watchdog_ms = 600000;
     // resident problem
     int N = 0, M = 0;
+    int maxdeg = 0;                // longest row (read back after the row-maximum pass)
     long long nnz = 0;
     bool has_vals = false;
     DevBuf stage_idx, stage_val, stage_mat, cols, vals, rowptr, rowmax, flags;
@@ -262,7 +264,10 @@ static int build_from_coo(sslapb_handle *h, const void *rows, const void *cols, 
     }
     if (val) {
         CK(h->rowmax.reserve(((size_t)n_rows + 1) * sizeof(double)));
-        CK(sslapb_launch_rowmax(h->rowptr.as<long long>(), h->vals.as<double>(), n_rows, h->rowmax.as<double>(), h->sms, h->stream));
+        CK(sslapb_launch_rowmax(h->rowptr.as<long long>(), h->vals.as<double>(), n_rows, h->rowmax.as<double>(), &h->flags.as<SslapbBuildFlags>()->maxdeg, h->sms, h->stream));
+        CK(cudaMemcpyAsync(&h->maxdeg, &h->flags.as<SslapbBuildFlags>()->maxdeg, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(h->ev[2], h->stream));
+        CK(cudaStreamSynchronize(h->stream));                 // the longest row picks the kernel instance (run_auction)
     }
     return SSLAPB_OK;
 }
@@ -300,7 +305,8 @@ static int build_from_dense(sslapb_handle *h, const double *mat, int32_t n_rows,
     CK(cudaMemcpyAsync(&F, h->flags.p, sizeof F, cudaMemcpyDeviceToHost, h->stream));
     if (want_vals) {
         CK(h->rowmax.reserve(((size_t)n_rows + 1) * sizeof(double)));
-        CK(sslapb_launch_rowmax(h->rowptr.as<long long>(), h->vals.as<double>(), n_rows, h->rowmax.as<double>(), h->sms, h->stream));
+        CK(sslapb_launch_rowmax(h->rowptr.as<long long>(), h->vals.as<double>(), n_rows, h->rowmax.as<double>(), &h->flags.as<SslapbBuildFlags>()->maxdeg, h->sms, h->stream));
+        CK(cudaMemcpyAsync(&h->maxdeg, &h->flags.as<SslapbBuildFlags>()->maxdeg, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaEventRecord(h->ev[2], h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -403,7 +409,7 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
     c.pmax_key = 0x8000000000000000ull;
     CK(cudaMemcpyAsync(P.ctrl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->ev[3], h->stream));
-    CK(sslapb_launch_auction(&P, h->grid, h->stream));
+    CK(sslapb_launch_auction(&P, h->grid, h->maxdeg > sslapb_coop_row_entries(), h->stream));
     CK(cudaEventRecord(h->ev[4], h->stream));
     std::vector<double> chosen((size_t)N);
     std::vector<int32_t> sol_tmp;

@@ -289,6 +289,19 @@ __device__ __forceinline__ int chain_rounds(const SslapbAuctionParams &P, double
 // person — it lost — or the owner it evicted, whose row was requested during the sweep), publishes (object, bid), and
 // after one barrier decides by itself whether it won (no serial merge); winners commit; after a second barrier every
 // warp derives the compacted list (push_all_left, auction_.pyx:137-162) redundantly from shared memory.
+#ifdef SSLAPB_LONG_ROWS
+// Very long rows (more than 8 warp passes; only in the kernel instance built with SSLAPB_LONG_ROWS, auction_long.cu): the
+// warp that owns such a bidder does not sweep it alone.  It flags the row as pending; the round's first barrier carries
+// the vote (BAR.RED.OR); if any row is pending ALL warps of the CTA sweep each pending row together — warp w takes the
+// 32-chunk trips w, w+16, ... (rotated per bidder), the partial top-2 go through shared memory — and the owner combines
+// them and publishes its bid (two more barriers, only in such rounds).  A dense 3162-entry row costs each warp 1-2 trips
+// per bidder instead of 25 dependent trips on the owner.
+#define SSLAPB_COOP_CHUNKS 256    // rows of more chunks (more than 8 warp passes, > ~1000 entries) are swept by the whole CTA
+__device__ __forceinline__ void coop_multi_pending(int a, int me, long long st, int dg, int *s_j);
+__device__ __forceinline__ void coop_multi_phase(const SslapbAuctionParams &P, double eps, const double *s_bounds, int nu, int a,
+                                                 bool pend, int me, long long st, int dg, int *s_j, double *s_bidv,
+                                                 SslapbBid &B, SslapbChunk &nxt, bool &nsingle, int &done);
+#endif
 __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double eps, const double *s_bounds, int nu, int *s_list,
                                             long long *s_start, int *s_deg, int *s_j, double *s_bidv, long long &its,
                                             long long max_iter, int &done, long long &rounds, int &me, long long &st,
@@ -310,9 +323,18 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
         B.j = -1; B.bid = 0.0; B.powner = -1; B.pdeg = 0; B.pstart = 0;
         SslapbChunk nxt = cur;
         bool nsingle = false;
+#ifdef SSLAPB_LONG_ROWS
+        bool pend = false;
+#endif
         if (active) {
             bool ok = single;
             if (ok) ok = sweep_single(P, cur, st, dg, eps, true, B, nxt, nsingle);
+#ifdef SSLAPB_LONG_ROWS
+            if (!ok && (((st + dg + 3) >> 2) - (st >> 2)) > SSLAPB_COOP_CHUNKS) {
+                pend = true;
+                if (lane == 0) coop_multi_pending(a, me, st, dg, s_j);
+            } else {
+#endif
             if (!ok) {                                         // long row (bound-pruned), or every candidate at -inf (exact, unpruned)
                 B = row_bid_rec<32>(P.cols, P.vals, P.rec, st, st + dg, lane, eps, s_bounds[0],
                                     single ? SSLAPB_NEG_INF : __ldg(P.rowmax + me) - s_bounds[1]);
@@ -323,8 +345,15 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
             }
             if (!ok) { B.j = -1; done = 4; }
             if (lane == 0) { s_j[a] = B.j; s_bidv[a] = B.bid; }
+#ifdef SSLAPB_LONG_ROWS
+            }
+#endif
         }
+#ifdef SSLAPB_LONG_ROWS
+        if (__syncthreads_or(pend)) coop_multi_phase(P, eps, s_bounds, nu, a, pend, me, st, dg, s_j, s_bidv, B, nxt, nsingle, done);
+#else
         __syncthreads();
+#endif
         int nme = me; long long nst = st; int ndg = dg; bool won = false;
         if (active) {                                          // merge (:375-385): do I hold the best bid on my object?
             const int oj = lane < nu ? s_j[lane] : -1;
@@ -400,12 +429,29 @@ __device__ __forceinline__ SslapbPartial row_partial_rec(const int *__restrict__
     int4 br = make_int4(0, 0, -1, 0);
     const long long c0 = start >> 2, c1 = (end + 3) >> 2;
     const int trips = (int)((c1 - c0 + 31) >> 5);
+#ifdef SSLAPB_LONG_ROWS
+    // software pipeline: the chunk of this warp's next trip is requested before the current one is processed (the rows
+    // of this instance take several trips per warp; the entries come from HBM, the records from L2)
+    long long chn = c0 + (long long)trip0 * 32 + lane;
+    int4 cjn = make_int4(0, 0, 0, 0);
+    double2 van = make_double2(0.0, 0.0), vbn = van;
+    if (trip0 < trips && chn < c1) { cjn = __ldg(c4 + chn); van = __ldg(v2 + 2 * chn); vbn = __ldg(v2 + 2 * chn + 1); }
+#pragma unroll 1
+    for (int it = trip0; it < trips; it += tstride) {
+        const long long ch = chn;
+        const int4 cj = cjn;
+        const double2 va = van, vb = vbn;
+        chn = ch + (long long)tstride * 32;
+        if (it + tstride < trips && chn < c1) { cjn = __ldg(c4 + chn); van = __ldg(v2 + 2 * chn); vbn = __ldg(v2 + 2 * chn + 1); }
+        if (ch >= c1) continue;
+#else
 #pragma unroll 1
     for (int it = trip0; it < trips; it += tstride) {
         const long long ch = c0 + (long long)it * 32 + lane;
         if (ch >= c1) continue;
         const int4 cj = __ldg(c4 + ch);
         const double2 va = __ldg(v2 + 2 * ch), vb = __ldg(v2 + 2 * ch + 1);
+#endif
         const int lo = (int)(start - (ch << 2)), hi = (int)min(end - (ch << 2), 4ll);
         const bool m0 = (0 >= lo) & (0 < hi) & (va.x >= thr), m1 = (1 >= lo) & (1 < hi) & (va.y >= thr);   // bound pruning
         const bool m2 = (2 >= lo) & (2 < hi) & (vb.x >= thr), m3 = (3 >= lo) & (3 < hi) & (vb.y >= thr);
@@ -463,6 +509,86 @@ __device__ __forceinline__ SslapbPartial row_partial_rec(const int *__restrict__
     o.br.z = __shfl_sync(SSLAPB_FULL, br.z, src); o.br.w = __shfl_sync(SSLAPB_FULL, br.w, src);
     return o;
 }
+
+#ifdef SSLAPB_LONG_ROWS
+struct SslapbCoopMulti {
+    SslapbPartial part[(SSLAPB_THREADS / 32) * (SSLAPB_THREADS / 32)];   // [bidder][sweeping warp]
+    long long st[SSLAPB_THREADS / 32];
+    int me[SSLAPB_THREADS / 32], dg[SSLAPB_THREADS / 32];
+};
+__device__ __forceinline__ SslapbCoopMulti *coop_multi_store()
+{
+    __shared__ SslapbCoopMulti s_cm;
+    return &s_cm;
+}
+__device__ __forceinline__ void coop_multi_pending(int a, int me, long long st, int dg, int *s_j)
+{
+    SslapbCoopMulti *cm = coop_multi_store();
+    cm->me[a] = me; cm->st[a] = st; cm->dg[a] = dg;
+    s_j[a] = -2;
+}
+// Warp-level combination of the per-warp partials of ONE row (lane l holds partial l; lanes without one hold "none").
+// Returns 0 and the bid in B; 1 when the bound-pruned result is not proven exact (fl(thr - pmin) < second-best fails: the
+// row must be swept again with every entry gathered); 2 when the row has no entry.
+__device__ __forceinline__ int combine_partials(const SslapbPartial &q, double eps, double thr, double pmin, SslapbBid &B)
+{
+    const unsigned bh = (unsigned)(q.bk >> 32), bl = (unsigned)q.bk;
+    const unsigned hi = __reduce_max_sync(SSLAPB_FULL, bh);
+    const unsigned lo = __reduce_max_sync(SSLAPB_FULL, bh == hi ? bl : 0u);
+    const bool top = (bh == hi) & (bl == lo);
+    const int widx = __reduce_max_sync(SSLAPB_FULL, top ? q.bi : -1);
+    const bool iswin = top & (q.bi == widx) & (q.bi >= 0);
+    const unsigned long long cand = iswin ? q.sk : q.bk;
+    const unsigned chh = (unsigned)(cand >> 32), chl = (unsigned)cand;
+    const unsigned shi = __reduce_max_sync(SSLAPB_FULL, chh);
+    const unsigned slo = __reduce_max_sync(SSLAPB_FULL, chh == shi ? chl : 0u);
+    const unsigned long long skey = ((unsigned long long)shi << 32) | slo;
+    const unsigned own = __ballot_sync(SSLAPB_FULL, iswin);
+    const double wi = skey > SSLAPB_KEY_NEG_INF ? sslapb_key2double(skey) : SSLAPB_NEG_INF;   // :344
+    if (thr > SSLAPB_NEG_INF && !((thr - pmin) < wi)) return 1;
+    if (own == 0u) return 2;
+    const int src = __ffs(own) - 1;
+    const double bc = __shfl_sync(SSLAPB_FULL, q.bc, src);
+    B.j = __shfl_sync(SSLAPB_FULL, q.bj, src);
+    const int sx = __shfl_sync(SSLAPB_FULL, q.br.x, src), sy = __shfl_sync(SSLAPB_FULL, q.br.y, src);
+    B.powner = __shfl_sync(SSLAPB_FULL, q.br.z, src);
+    B.pdeg = __shfl_sync(SSLAPB_FULL, q.br.w, src);
+    B.pstart = (long long)(((unsigned long long)(unsigned)sy << 32) | (unsigned)sx);
+    B.bid = (bc - wi) + eps;                                   // :360
+    return 0;
+}
+// after the round's first barrier, by every warp of the CTA (a = warp index = list position it owns, if any)
+__device__ __forceinline__ void coop_multi_phase(const SslapbAuctionParams &P, double eps, const double *s_bounds, int nu, int a,
+                                                 bool pend, int me, long long st, int dg, int *s_j, double *s_bidv,
+                                                 SslapbBid &B, SslapbChunk &nxt, bool &nsingle, int &done)
+{
+    constexpr int NW = SSLAPB_THREADS / 32;
+    const int lane = threadIdx.x & 31;
+    SslapbCoopMulti *cm = coop_multi_store();
+    for (int a2 = 0; a2 < nu; ++a2) {
+        if (s_j[a2] != -2) continue;
+        const long long st2 = cm->st[a2];
+        const SslapbPartial part = row_partial_rec(P.cols, P.vals, P.rec, st2, st2 + cm->dg[a2], lane, (a + 5 * a2) & (NW - 1), NW,
+                                                   __ldg(P.rowmax + cm->me[a2]) - s_bounds[1]);
+        if (lane == 0) cm->part[a2 * NW + a] = part;
+    }
+    __syncthreads();
+    if (pend) {
+        SslapbPartial q;
+        q.bk = 0ull; q.sk = 0ull; q.bc = 0.0; q.bi = -1; q.bj = -1; q.br = make_int4(0, 0, -1, 0);
+        if (lane < NW) q = cm->part[a * NW + lane];
+        if (combine_partials(q, eps, __ldg(P.rowmax + me) - s_bounds[1], s_bounds[0], B))
+            B = row_bid_rec<32>(P.cols, P.vals, P.rec, st, st + dg, lane, eps);   // pruning unproven: gather everything
+        const bool ok = B.j >= 0;
+        const long long n0 = B.pstart >> 2, n1 = (B.pstart + B.pdeg + 3) >> 2;
+        nsingle = (n1 - n0) <= 32;
+        nxt = sslapb_load_chunk(P.cols, P.vals, n0 + lane, ok && B.powner >= 0 && nsingle && (n0 + lane < n1));
+        if (!ok) { B.j = -1; done = 4; }
+        if (lane == 0) { s_j[a] = B.j; s_bidv[a] = B.bid; }
+    }
+    __syncthreads();
+}
+#endif
 
 // executed by ALL warps of CTA 0 while the single bidder's row is long; warp 0 carries the list entry in (li, lst, ldg)
 __device__ __forceinline__ int coop_chain_rounds(const SslapbAuctionParams &P, double eps, double pmin, double spread,
@@ -653,6 +779,9 @@ __device__ __forceinline__ int block_excl_scan_flag(bool flag, int &total)
 
 #define GB() do { if (!grid_barrier(C, nblk, bar_epoch, P.watchdog_ns)) return; } while (0)
 
+#ifdef SSLAPB_LONG_ROWS
+#define sslapb_auction_kernel sslapb_auction_kernel_long   // second instance of the kernel, see auction_long.cu
+#endif
 __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(SslapbAuctionParams P)
 {
     SslapbCtrl *C = P.ctrl;
@@ -937,6 +1066,15 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
     }
 }
 
+#ifdef SSLAPB_LONG_ROWS
+// only the cooperative launch: the state is initialised by sslapb_launch_auction (auction.cu)
+extern "C" cudaError_t sslapb_launch_auction_long(const SslapbAuctionParams *P, int grid, cudaStream_t stream)
+{
+    void *args[] = {(void *)P};
+    return cudaLaunchCooperativeKernel((const void *)sslapb_auction_kernel, dim3(grid), dim3(SSLAPB_THREADS), args, 0, stream);
+}
+extern "C" int sslapb_coop_row_entries() { return 4 * SSLAPB_COOP_CHUNKS - 3; }
+#else
 // ----------------------------------------------------------------------------------------------------------------------
 // Stand-alone bidding sweep (non-cooperative): the grid regime's step (1) for an explicit bidder list.  Used for
 // kernel-level parity (bit-exact (jbest, bid) against the oracle) and for the HBM-roofline measurement of the CSR sweep.
@@ -1003,9 +1141,12 @@ __global__ void sslapb_auction_init_kernel(SslapbAuctionParams P)
     }
 }
 
-extern "C" cudaError_t sslapb_launch_auction(const SslapbAuctionParams *P, int grid, cudaStream_t stream)
+extern "C" cudaError_t sslapb_launch_auction_long(const SslapbAuctionParams *P, int grid, cudaStream_t stream);
+// long_rows: the longest row exceeds sslapb_coop_row_entries() entries -> the kernel instance of auction_long.cu
+extern "C" cudaError_t sslapb_launch_auction(const SslapbAuctionParams *P, int grid, int long_rows, cudaStream_t stream)
 {
     sslapb_auction_init_kernel<<<grid, 1024, 0, stream>>>(*P);
+    if (long_rows) return sslapb_launch_auction_long(P, grid, stream);
     void *args[] = {(void *)P};
     return cudaLaunchCooperativeKernel((const void *)sslapb_auction_kernel, dim3(grid), dim3(SSLAPB_THREADS), args, 0, stream);
 }
@@ -1291,3 +1432,5 @@ extern "C" cudaError_t sslapb_launch_auction_batch(const SslapbBatchParams *B, c
     sslapb_auction_batch_kernel<<<grid, 32 * warps_per_cta, 0, stream>>>(*B);
     return cudaGetLastError();
 }
+
+#endif  // !SSLAPB_LONG_ROWS

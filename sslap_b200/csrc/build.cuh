@@ -5,7 +5,7 @@ struct SslapbBuildFlags {
     int unsorted;                 // rows not non-decreasing (the reference's precondition, auction_.pyx:33-48)
     int out_of_range;             // index outside [0,N) x [0,M)
     int empty_rows;               // some row in [0,N) has no entry (infeasible; UB in the reference)
-    int pad;
+    int maxdeg;                   // longest row (written by the row-maximum pass)
     unsigned long long maxabs;    // bits of max |a_ij| (non-negative doubles order like uint64), max_val :123-134
     long long nnz;                // dense path: number of valid (>= 0) entries
 };

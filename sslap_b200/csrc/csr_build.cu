@@ -180,8 +180,9 @@ extern "C" cudaError_t sslapb_launch_index_max(const void *rows, const void *col
 // per-row maximum of the (sign-folded) values: warp per row
 __global__ void __launch_bounds__(256) sslapb_rowmax_kernel(const long long *__restrict__ rowptr,
                                                             const double *__restrict__ vals, long long nrows,
-                                                            double *__restrict__ rowmax)
+                                                            double *__restrict__ rowmax, int *maxdeg)
 {
+    int dmax = 0;
     const int lane = threadIdx.x & 31;
     const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long r = gwarp; r < nrows; r += nwarps) {
@@ -190,13 +191,15 @@ __global__ void __launch_bounds__(256) sslapb_rowmax_kernel(const long long *__r
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(SSLAPB_FULL, m, off));
         if (lane == 0) rowmax[r] = m;
+        dmax = max(dmax, (int)min(rowptr[r + 1] - rowptr[r], 0x7fffffffll));
     }
+    if (lane == 0 && dmax > 0) atomicMax(maxdeg, dmax);
 }
 
 extern "C" cudaError_t sslapb_launch_rowmax(const long long *rowptr, const double *vals, long long nrows, double *rowmax,
-                                            int sms, cudaStream_t stream)
+                                            int *maxdeg, int sms, cudaStream_t stream)
 {
-    sslapb_rowmax_kernel<<<sms * 8, 256, 0, stream>>>(rowptr, vals, nrows, rowmax);
+    sslapb_rowmax_kernel<<<sms * 8, 256, 0, stream>>>(rowptr, vals, nrows, rowmax, maxdeg);
     return cudaGetLastError();
 }
 
