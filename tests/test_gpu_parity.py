@@ -366,6 +366,38 @@ def test_long_rows_take_the_generic_sweep(gpu, oracle_mod):
         assert_meta_equal(got["meta"], want["meta"])
 
 
+def test_very_long_rows_use_the_cooperative_kernel_instance(gpu, oracle_mod):
+    """Rows of more than 1021 entries select the second instance of the persistent kernel (auction_long.cu), where the
+    whole CTA sweeps such rows in the multi-bidder regime: dense inputs, a rectangular one, and a sparse problem with a
+    few dense rows (pending and ordinary bidders in the same round)."""
+    sslap_b200, nat, h = gpu
+    rng = np.random.default_rng(33)
+    cases = []
+    cases.append(("dense-int", rng.integers(1, 200, (1100, 1100)).astype(np.float64), "min"))
+    cases.append(("dense-float", rng.uniform(0, 100, (1300, 1300)), "max"))
+    rect = rng.uniform(0, 50, (1050, 1500))
+    rect[rng.random(rect.shape) < 0.05] = -1
+    cases.append(("rect", rect, "max"))
+    mixed = -np.ones((2500, 2500))
+    mask = rng.random(mixed.shape) < 0.01
+    mixed[mask] = rng.uniform(0, 100, int(mask.sum()))
+    mixed[np.arange(2500), rng.permutation(2500)] = rng.uniform(0, 100, 2500)
+    for r in (3, 700, 701, 1500, 2499):
+        mixed[r] = rng.uniform(0, 100, 2500)
+    cases.append(("mixed", mixed, "max"))
+    for name, mat, problem in cases:
+        want = oracle_mod.auction_solve(mat=mat, problem=problem, return_prices=True)
+        for t_small in (32, 4):
+            h.set_option("t_small", t_small)
+            try:
+                got = sslap_b200.auction_solve(mat=mat.copy(), problem=problem, cardinality_check=False)
+            finally:
+                h.set_option("t_small", 32)
+            assert np.array_equal(got["sol"], want["sol"]), name
+            assert_meta_equal(got["meta"], want["meta"])
+            assert np.array_equal(prices_of(nat, h, mat.shape[1]), want["prices"]), name
+
+
 def test_randomized_differential_against_the_oracle(gpu, oracle_mod):
     """120 seeded random instances across shapes, densities, cost kinds, objectives, eps options, iteration caps and
     regime splits: `sol` and the integer meta keys must equal the oracle's bit for bit; so must the float64 prices."""
