@@ -63,16 +63,18 @@ typedef struct sslapb_meta {
     int64_t nnz;
     int64_t rounds_grid, rounds_warp, rounds_solo;   /* rounds executed per regime */
     float   prof_ms[8];      /* device time by section: grid bid, grid assign, grid compaction, warp regime, solo regime,
-                                eCE + phase change, (unused), grid barriers */
+                                eCE + phase change, cluster regime, grid barriers */
     int64_t prune_second_pass; /* grid-regime rows whose bound-pruned sweep needed the second (exactness) gather pass */
     int32_t stop_reason;     /* 1 target-eps CS holds (:275) | 2 eps < target (:280) | 3 max_iter (:309) */
-    int32_t pad;
+    int32_t rounds_cluster;  /* rounds run by cluster 0 alone (mid-sized frontiers); the others are in rounds_grid/warp/solo */
 } sslapb_meta;
 
 int  sslapb_create(int device, sslapb_handle **out);
 void sslapb_destroy(sslapb_handle *h);
 const char *sslapb_last_error(const sslapb_handle *h);
-/* tuning knobs: "t_small" (frontier size at or below which CTA 0 runs rounds alone, 0..32), "watchdog_ms" */
+/* tuning knobs: "t_small" (frontier size at or below which CTA 0 runs rounds alone, 0..32), "t_cluster" (frontier size
+   at or below which one thread-block cluster of 8 CTAs runs the rounds with hardware cluster barriers; 0 = off, the
+   default — opt-in), "watchdog_ms" (device watchdog of a single barrier wait, default 120000) */
 int  sslapb_set_option(sslapb_handle *h, const char *name, int64_t value);
 
 /* Pinned host memory for callers that want asynchronous staging (bench.py's e2e leg). */

@@ -27,7 +27,7 @@ class Meta(C.Structure):
                 ("cardinality", C.c_int32), ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("nnz", C.c_int64),
                 ("rounds_grid", C.c_int64), ("rounds_warp", C.c_int64), ("rounds_solo", C.c_int64),
                 ("prof_ms", C.c_float * 8), ("prune_second_pass", C.c_int64),
-                ("stop_reason", C.c_int32), ("pad", C.c_int32)]
+                ("stop_reason", C.c_int32), ("rounds_cluster", C.c_int32)]
 
 
 _lib = None

@@ -24,9 +24,10 @@ cudaError_t sslapb_launch_index_max(const void *, const void *, int, long long, 
 cudaError_t sslapb_launch_dense_count(const double *, int, int, long long *, SslapbBuildFlags *, int, cudaStream_t);
 cudaError_t sslapb_launch_dense_fill(const double *, int, int, int, const long long *, int *, double *,
                                      SslapbBuildFlags *, int, cudaStream_t);
-cudaError_t sslapb_launch_auction(const SslapbAuctionParams *, int, int, cudaStream_t);
+cudaError_t sslapb_launch_auction(const SslapbAuctionParams *, int, int, int, cudaStream_t);
 int sslapb_coop_row_entries();
 cudaError_t sslapb_auction_grid_size(int, int *);
+cudaError_t sslapb_auction_cluster_grid(int, int *, int *);
 cudaError_t sslapb_launch_bid_sweep(const SslapbAuctionParams *, const int *, int, float, int, int, cudaStream_t);
 cudaError_t sslapb_launch_sweep_plan(const SslapbAuctionParams *, int, int *, cudaStream_t);
 cudaError_t sslapb_launch_bid_sweep_tma(const SslapbAuctionParams *, const int *, float, int, int, cudaStream_t);
@@ -90,7 +91,11 @@ struct sslapb_handle {
     cudaEvent_t ev[6] = {};
     std::string err;
     int t_small = 32;
-    long long watchdog_ms = 600000;
+    int t_cluster = 0;             // frontier size up to which cluster 0 runs the rounds alone; 0 = regime off (default):
+                                   // the launch is then the plain cooperative one, one CTA on every SM
+    int cluster = 1;               // CTAs per cluster the device supports for the persistent kernel (1: none)
+    int cluster_grid = 0;          // grid of the cluster launch (a multiple of `cluster`)
+    long long watchdog_ms = 120000;
     // resident problem
     int N = 0, M = 0;
     int maxdeg = 0;                // longest row (read back after the row-maximum pass)
@@ -138,6 +143,7 @@ extern "C" int sslapb_create(int device, sslapb_handle **out)
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete h; return -(int)e; }
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     if ((e = sslapb_auction_grid_size(device, &h->grid)) != cudaSuccess) { delete h; return -(int)e; }
+    if ((e = sslapb_auction_cluster_grid(device, &h->cluster_grid, &h->cluster)) != cudaSuccess) { delete h; return -(int)e; }
     *out = h;
     return SSLAPB_OK;
 }
@@ -162,6 +168,7 @@ extern "C" const char *sslapb_last_error(const sslapb_handle *h) { return h ? h-
 extern "C" int sslapb_set_option(sslapb_handle *h, const char *name, int64_t value)
 {
     if (!h || !name) return SSLAPB_E_BAD_ARG;
+    if (!strcmp(name, "t_cluster")) { if (value < 0 || value > (1 << 20)) return SSLAPB_E_BAD_ARG; h->t_cluster = (int)value; return 0; }
     if (!strcmp(name, "t_small")) { if (value < 0 || value > 32) return SSLAPB_E_BAD_ARG; h->t_small = (int)value; return 0; }
     if (!strcmp(name, "watchdog_ms")) { if (value <= 0) return SSLAPB_E_BAD_ARG; h->watchdog_ms = value; return 0; }
     return fail(h, SSLAPB_E_BAD_ARG, std::string("unknown option ") + name);
@@ -373,7 +380,7 @@ static int reserve_auction_state(sslapb_handle *h, SslapbAuctionParams &P)
     const size_t N = (size_t)h->N, M = (size_t)h->M;
     CK(h->price.reserve(M * 8)); CK(h->owner.reserve(M * sizeof(SslapbObjRec))); CK(h->p2o.reserve(N * 4));
     CK(h->list.reserve(N * 4)); CK(h->mover.reserve(N * 4)); CK(h->bidj.reserve(N * 4)); CK(h->bidv.reserve(N * 8));
-    CK(h->bidkey.reserve(M * 8)); CK(h->winpos.reserve(M * 4)); CK(h->hole_count.reserve((size_t)h->grid * 4 + 64));
+    CK(h->bidkey.reserve(M * 8)); CK(h->winpos.reserve(M * 4)); CK(h->hole_count.reserve((size_t)h->sms * 4 + 64));
     CK(h->chosen.reserve(N * 8)); CK(h->ctrl.reserve(sizeof(SslapbCtrl)));
     P.N = h->N; P.M = h->M;
     P.rowptr = h->rowptr.as<long long>(); P.cols = h->cols.as<int>(); P.vals = h->vals.as<double>();
@@ -383,6 +390,10 @@ static int reserve_auction_state(sslapb_handle *h, SslapbAuctionParams &P)
     P.bidkey = h->bidkey.as<unsigned long long>(); P.winpos = h->winpos.as<int>();
     P.hole_count = h->hole_count.as<int>(); P.chosen = h->chosen.as<double>(); P.ctrl = h->ctrl.as<SslapbCtrl>();
     P.t_small = h->t_small;
+    // opt-in: launch in clusters, a few SMs stay empty (not combined with the long-row instance)
+    const bool use_cluster = h->cluster > 1 && h->t_cluster > 0 && !(h->maxdeg > sslapb_coop_row_entries());
+    P.cluster = use_cluster ? h->cluster : 1;
+    P.t_cluster = use_cluster ? h->t_cluster : 0;
     P.watchdog_ns = (unsigned long long)h->watchdog_ms * 1000000ull;
     return SSLAPB_OK;
 }
@@ -409,7 +420,7 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
     c.pmax_key = 0x8000000000000000ull;
     CK(cudaMemcpyAsync(P.ctrl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->ev[3], h->stream));
-    CK(sslapb_launch_auction(&P, h->grid, h->maxdeg > sslapb_coop_row_entries(), h->stream));
+    CK(sslapb_launch_auction(&P, P.cluster > 1 ? h->cluster_grid : h->grid, P.cluster, h->maxdeg > sslapb_coop_row_entries(), h->stream));
     CK(cudaEventRecord(h->ev[4], h->stream));
     std::vector<double> chosen((size_t)N);
     std::vector<int32_t> sol_tmp;
@@ -442,6 +453,7 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
         cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); meta->h2d_ms = ms;
         meta->n_rows = h->N; meta->n_cols = h->M; meta->nnz = h->nnz;
         meta->rounds_grid = c.rounds_grid; meta->rounds_warp = c.rounds_warp; meta->rounds_solo = c.rounds_solo;
+        meta->rounds_cluster = (int32_t)c.rounds_cluster;
         for (int k = 0; k < 8; ++k) meta->prof_ms[k] = (float)((double)c.prof[k] * 1e-6);
         meta->stop_reason = c.done;
         meta->prune_second_pass = c.prune_second_pass;
@@ -579,8 +591,8 @@ extern "C" int sslapb_bid_sweep(sslapb_handle *h, const double *prices, const in
     const bool streamed = !d_bidders && nb == h->N && (merge & 4);
     merge &= 3;
     if (streamed) {
-        CK(h->sweep_plan.reserve(((size_t)h->grid + 2) * 4));
-        CK(sslapb_launch_sweep_plan(&P, h->grid, h->sweep_plan.as<int>(), h->stream));
+        CK(h->sweep_plan.reserve(((size_t)h->sms + 2) * 4));
+        CK(sslapb_launch_sweep_plan(&P, h->sms, h->sweep_plan.as<int>(), h->stream));
     }
     const size_t flush_bytes = (size_t)256 << 20;
     if (flush_l2) CK(h->flush.reserve(flush_bytes));
@@ -589,8 +601,8 @@ extern "C" int sslapb_bid_sweep(sslapb_handle *h, const double *prices, const in
         if (merge) CK(cudaMemsetAsync(P.bidkey, 0, (size_t)h->M * 8, h->stream));
         if (flush_l2) CK(cudaMemsetAsync(h->flush.p, it & 0xff, flush_bytes, h->stream));
         CK(cudaEventRecord(h->ev[3], h->stream));
-        if (streamed) CK(sslapb_launch_bid_sweep_tma(&P, h->sweep_plan.as<int>(), eps, merge, h->grid, h->stream));
-        else CK(sslapb_launch_bid_sweep(&P, d_bidders, nb, eps, merge, h->grid, h->stream));
+        if (streamed) CK(sslapb_launch_bid_sweep_tma(&P, h->sweep_plan.as<int>(), eps, merge, h->sms, h->stream));
+        else CK(sslapb_launch_bid_sweep(&P, d_bidders, nb, eps, merge, h->sms, h->stream));
         CK(cudaEventRecord(h->ev[4], h->stream));
         CK(cudaStreamSynchronize(h->stream));
         float ms = 0.f;

@@ -777,10 +777,183 @@ __device__ __forceinline__ int block_excl_scan_flag(bool flag, int &total)
     return s_wtot[warp] + inwarp;
 }
 
+// One Jacobi round with the bidders spread over several CTAs (auction_.pyx:337-430) — by the whole grid (grid barriers) or,
+// for mid-sized frontiers, by the CTAs of cluster 0 alone (hardware cluster barriers, ~0.25 us instead of ~1.5 us each;
+// the other CTAs wait at one grid barrier for the cluster to hand the phase over).
+struct SslapbScope { int blk, nblk, gwarp, nwarps; bool lead; };   // CTA rank / count, warp rank / count, the one reporting thread
+template <bool CLUSTER>
+__device__ __forceinline__ bool round_barrier(SslapbCtrl *C, unsigned nblk, unsigned &epoch, unsigned long long watchdog_ns)
+{
+    if (CLUSTER) {
+        // block barrier first (every warp converged, CTA-local hazards closed), then the hardware cluster barrier in its
+        // non-.aligned form: an opaque asm gives the compiler no reason to reconverge a warp in front of it
+        __syncthreads();
+        asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+        return true;
+    }
+    return grid_barrier(C, nblk, epoch, watchdog_ns);
+}
+template <bool CLUSTER>
+__device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, SslapbCtrl *C, const SslapbScope S, int nu, float eps_f,
+                                             long long its, long long max_iter, double pmin, double spread, unsigned &bar_epoch)
+{
+    __shared__ int s_red, s_tie;
+    __shared__ int s_hpre[3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(SSLAPB_FULL, tid >> 5, 0);
+    {
+    
+    const double eps = (double)eps_f;
+    unsigned long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0, tp5 = 0;
+    if (S.lead) tp0 = sslapb_globaltimer();
+    int n2nd = 0;
+    // (1) bidding: warp per list position (auction_.pyx:339-365) + per-object atomicMax merge (:375-385)
+    auto emit_bid = [&](int a, int j, double bid) {
+                        if (lane == 0) {
+                            P.bidj[a] = j;
+                            P.bidv[a] = bid;
+                            if (j >= 0) {
+                                const unsigned long long key = sslapb_ord64(bid);
+                                const unsigned long long old = atomicMax(P.bidkey + j, key);
+                                if (old == key) *(volatile int *)&C->tie_flag = 1;
+                            } else {
+                                *(volatile int *)&C->abort_flag = 2;   // empty row: rejected at CSR build
+                            }
+                        }
+                    };
+    // (a software pipeline across rows was measured to buy nothing: the sweep is instruction-issue bound)
+    for (int a = S.gwarp; a < nu; a += S.nwarps) {
+        int v = P.list[a];
+        if (v < -1) { v = P.mover[-(v + 2)]; if (lane == 0) P.list[a] = v; }   // hole filled by the last compaction
+        const long long st = __ldg(P.rowptr + v), en = __ldg(P.rowptr + v + 1);
+        int j; double bid;
+        if ((((en + 3) >> 2) - (st >> 2)) <= 32) {
+            const SslapbStreamChunk c = sslapb_stream_chunk(P.cols, P.vals, st, en, lane);
+            const SslapbBid o = row_bid_pruned(c, P.price, st, en, lane, eps, pmin, __ldg(P.rowmax + v) - spread, n2nd);
+            j = o.j; bid = o.bid;
+            // every candidate at -inf (objects priced +inf by single-choice bidders): the exact generic sweep decides
+            if (j < 0) row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);
+        } else {                                       // long row: multi-trip sweep, same bound pruning
+            row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid, pmin, __ldg(P.rowmax + v) - spread);
+        }
+        emit_bid(a, j, bid);
+    }
+    if (n2nd && lane == 0) atomicAdd((unsigned long long *)&C->prune_second_pass, (unsigned long long)n2nd);
+    if (S.lead) tp1 = sslapb_globaltimer();
+    if (!round_barrier<CLUSTER>(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return false;
+    if (S.lead) tp2 = sslapb_globaltimer();
+    if (tid == 0) s_tie = *(volatile int *)&C->tie_flag;
+    __syncthreads();
+    const int tie = __shfl_sync(SSLAPB_FULL, s_tie, 0);
+    const int L = (nu + S.nblk - 1) / S.nblk;    // each CTA owns a contiguous chunk of positions
+    const int lo = min(nu, S.blk * L), hi = min(nu, lo + L);
+    if (tie) {                                         // (1b) equal best bids: earliest list position wins (:379)
+        for (int a = lo + tid; a < hi; a += blockDim.x) {
+            const int j = P.bidj[a];
+            if (P.bidkey[j] == sslapb_ord64(P.bidv[a])) atomicMin(P.winpos + j, a);
+        }
+        if (!round_barrier<CLUSTER>(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return false;
+    }
+    // (2) assignment (:394-427), by the winner's own list position
+    int myholes = 0;
+    for (int a = lo + tid; a < hi; a += blockDim.x) {
+        const int j = P.bidj[a];
+        const double bid = P.bidv[a];
+        const bool win = (P.bidkey[j] == sslapb_ord64(bid)) && (!tie || P.winpos[j] == a);
+        if (win) {
+            const int i = P.list[a];
+            const int prev = P.rec[j].owner;
+            SslapbObjRec r;
+            r.start = __ldg(P.rowptr + i); r.owner = i; r.deg = (int)(__ldg(P.rowptr + i + 1) - r.start);
+            r.price = bid; r.pad = 0;
+            *reinterpret_cast<int4 *>(P.rec + j) = *reinterpret_cast<const int4 *>(&r);
+            P.rec[j].price = bid;
+            P.price[j] = bid;
+            P.p2o[i] = j;
+            if (prev >= 0) P.p2o[prev] = -1; else ++myholes;
+            P.list[a] = prev;                          // evicted owner takes the slot, or -1 = hole
+            P.bidkey[j] = 0ull;
+            if (tie) P.winpos[j] = 0x7fffffff;
+        }
+    }
+    if (tid == 0) s_red = 0;
+    __syncthreads();
+    if (myholes) atomicAdd(&s_red, myholes);
+    __syncthreads();
+    if (tid == 0) P.hole_count[S.blk] = s_red;
+    if (S.lead) tp3 = sslapb_globaltimer();
+    if (!round_barrier<CLUSTER>(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return false;
+    if (S.lead) tp4 = sslapb_globaltimer();
+    // (3) push_all_left (:137-162): k-th hole left of new_nu <- k-th live entry right of it
+    if (warp == 0) {                                   // per-CTA hole counts -> total, my prefix, prefix of the split chunk
+        int ht = 0, hp = 0;
+        for (int b = lane; b < S.nblk; b += 32) {
+            const int h = P.hole_count[b];
+            ht += h;
+            if (b < S.blk) hp += h;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            ht += __shfl_xor_sync(SSLAPB_FULL, ht, off);
+            hp += __shfl_xor_sync(SSLAPB_FULL, hp, off);
+        }
+        const int cb0 = (nu - ht) / L;
+        int h2 = 0;
+        for (int b = lane; b < cb0; b += 32) h2 += P.hole_count[b];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) h2 += __shfl_xor_sync(SSLAPB_FULL, h2, off);
+        if (lane == 0) { s_hpre[0] = h2; s_hpre[1] = hp; s_hpre[2] = ht; s_red = 0; }
+    }
+    __syncthreads();
+    const int H = __shfl_sync(SSLAPB_FULL, s_hpre[2], 0), hpre = __shfl_sync(SSLAPB_FULL, s_hpre[1], 0);
+    const int new_nu = nu - H;
+    const int cb = new_nu / L;                         // chunk that contains the split point
+    int cnt = 0;
+    for (int a = cb * L + tid; a < new_nu; a += blockDim.x) cnt += (P.list[a] < 0);
+    if (cnt) atomicAdd(&s_red, cnt);
+    __syncthreads();
+    const int Hsplit = s_hpre[0] + s_red;              // holes in [0,new_nu)
+    __syncthreads();
+    int run = hpre;                                    // holes in [0, tile start)
+    for (int base = lo; base < hi; base += blockDim.x) {
+        const int a = base + tid;
+        int v = 0;
+        bool hole = false;
+        if (a < hi) { v = P.list[a]; hole = v < 0; }
+        int ttot;
+        const int before = run + block_excl_scan_flag(hole, ttot);
+        if (a < hi) {
+            if (a < new_nu) {
+                if (hole) P.list[a] = -(before + 2);   // rank-encoded; decoded by the next reader
+            } else if (!hole) {
+                P.mover[(a - new_nu) - (before - Hsplit)] = v;
+            }
+        }
+        run += ttot;
+    }
+    if (S.lead) {
+        C->nu = new_nu;
+        C->its = its + 1;
+        C->tie_flag = 0;
+        if (CLUSTER) C->rounds_cluster += 1; else C->rounds_grid += 1;
+        if (its + 1 >= max_iter) C->done = 3;
+        tp5 = sslapb_globaltimer();
+    }
+    if (!round_barrier<CLUSTER>(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return false;
+    if (S.lead && !CLUSTER) {
+        C->prof[0] += tp1 - tp0; C->prof[1] += tp3 - tp2; C->prof[2] += tp5 - tp4;
+        C->prof[7] += (tp2 - tp1) + (tp4 - tp3) + (sslapb_globaltimer() - tp5);
+    }
+    }
+    return true;
+}
+
 #define GB() do { if (!grid_barrier(C, nblk, bar_epoch, P.watchdog_ns)) return; } while (0)
 
 #ifdef SSLAPB_LONG_ROWS
 #define sslapb_auction_kernel sslapb_auction_kernel_long   // second instance of the kernel, see auction_long.cu
+#endif
+#ifdef SSLAPB_CLUSTER_REGIME
+#define sslapb_auction_kernel sslapb_auction_kernel_cluster   // third instance, see auction_cluster.cu
 #endif
 __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(SslapbAuctionParams P)
 {
@@ -792,8 +965,6 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
     const int nwarps = nblk * wpc;
     const int gtid = blockIdx.x * blockDim.x + tid;
     const int nthreads = nblk * blockDim.x;
-    __shared__ int s_red;
-    __shared__ int s_hpre[3];
     __shared__ struct { int nu, done, nred, tie; float eps; long long its, max_iter; unsigned long long pmin0, pmin1, pmax; } s_top;
     unsigned bar_epoch = 0;                                    // barriers passed so far * #CTAs (wraps harmlessly)
 
@@ -828,149 +999,36 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
         __syncthreads();                                       // s_top is rewritten only after every thread has read it
         if (done) break;
 
+#ifdef SSLAPB_CLUSTER_REGIME
+        if (nu > P.t_small && nu > P.t_cluster) {
+#else
         if (nu > P.t_small) {
+#endif
             // ================================ grid regime: one round ================================
-            const double eps = (double)eps_f;
-            unsigned long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0, tp5 = 0;
-            if (gtid == 0) tp0 = sslapb_globaltimer();
-            int n2nd = 0;
-            // (1) bidding: warp per list position (auction_.pyx:339-365) + per-object atomicMax merge (:375-385)
-            auto emit_bid = [&](int a, int j, double bid) {
-                                if (lane == 0) {
-                                    P.bidj[a] = j;
-                                    P.bidv[a] = bid;
-                                    if (j >= 0) {
-                                        const unsigned long long key = sslapb_ord64(bid);
-                                        const unsigned long long old = atomicMax(P.bidkey + j, key);
-                                        if (old == key) *(volatile int *)&C->tie_flag = 1;
-                                    } else {
-                                        *(volatile int *)&C->abort_flag = 2;   // empty row: rejected at CSR build
-                                    }
-                                }
-                            };
-            // (a software pipeline across rows was measured to buy nothing: the sweep is instruction-issue bound)
-            for (int a = gwarp; a < nu; a += nwarps) {
-                int v = P.list[a];
-                if (v < -1) { v = P.mover[-(v + 2)]; if (lane == 0) P.list[a] = v; }   // hole filled by the last compaction
-                const long long st = __ldg(P.rowptr + v), en = __ldg(P.rowptr + v + 1);
-                int j; double bid;
-                if ((((en + 3) >> 2) - (st >> 2)) <= 32) {
-                    const SslapbStreamChunk c = sslapb_stream_chunk(P.cols, P.vals, st, en, lane);
-                    const SslapbBid o = row_bid_pruned(c, P.price, st, en, lane, eps, pmin, __ldg(P.rowmax + v) - spread, n2nd);
-                    j = o.j; bid = o.bid;
-                    // every candidate at -inf (objects priced +inf by single-choice bidders): the exact generic sweep decides
-                    if (j < 0) row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);
-                } else {                                       // long row: multi-trip sweep, same bound pruning
-                    row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid, pmin, __ldg(P.rowmax + v) - spread);
+            const SslapbScope S = {(int)blockIdx.x, (int)nblk, gwarp, nwarps, gtid == 0};
+            if (!spread_round<false>(P, C, S, nu, eps_f, its, max_iter, pmin, spread, bar_epoch)) return;
+#ifdef SSLAPB_CLUSTER_REGIME
+        } else if (nu > P.t_small) {
+            // ================================ cluster regime: cluster 0 runs rounds until nu <= t_small ================================
+            if ((int)blockIdx.x < P.cluster) {
+                unsigned long long tc0 = 0;
+                if (gtid == 0) tc0 = sslapb_globaltimer();
+                const SslapbScope S = {(int)blockIdx.x, P.cluster, gwarp, P.cluster * wpc, gtid == 0};
+                int cnu = nu, cdone = 0;
+                long long cits = its;
+                while (!cdone && cnu > P.t_small) {
+                    spread_round<true>(P, C, S, cnu, eps_f, cits, max_iter, pmin, spread, bar_epoch);
+                    if (tid == 0) { s_top.nu = *(volatile int *)&C->nu; s_top.done = *(volatile int *)&C->done; s_top.its = *(volatile long long *)&C->its; }
+                    __syncthreads();
+                    cnu = __shfl_sync(SSLAPB_FULL, s_top.nu, 0);
+                    cdone = __shfl_sync(SSLAPB_FULL, s_top.done, 0);
+                    cits = s_top.its;
+                    __syncthreads();
                 }
-                emit_bid(a, j, bid);
-            }
-            if (n2nd && lane == 0) atomicAdd((unsigned long long *)&C->prune_second_pass, (unsigned long long)n2nd);
-            if (gtid == 0) tp1 = sslapb_globaltimer();
-            GB();
-            if (gtid == 0) tp2 = sslapb_globaltimer();
-            if (tid == 0) s_top.tie = *(volatile int *)&C->tie_flag;
-            __syncthreads();
-            const int tie = __shfl_sync(SSLAPB_FULL, s_top.tie, 0);
-            const int L = (nu + (int)nblk - 1) / (int)nblk;    // each CTA owns a contiguous chunk of positions
-            const int lo = min(nu, (int)blockIdx.x * L), hi = min(nu, lo + L);
-            if (tie) {                                         // (1b) equal best bids: earliest list position wins (:379)
-                for (int a = lo + tid; a < hi; a += blockDim.x) {
-                    const int j = P.bidj[a];
-                    if (P.bidkey[j] == sslapb_ord64(P.bidv[a])) atomicMin(P.winpos + j, a);
-                }
-                GB();
-            }
-            // (2) assignment (:394-427), by the winner's own list position
-            int myholes = 0;
-            for (int a = lo + tid; a < hi; a += blockDim.x) {
-                const int j = P.bidj[a];
-                const double bid = P.bidv[a];
-                const bool win = (P.bidkey[j] == sslapb_ord64(bid)) && (!tie || P.winpos[j] == a);
-                if (win) {
-                    const int i = P.list[a];
-                    const int prev = P.rec[j].owner;
-                    SslapbObjRec r;
-                    r.start = __ldg(P.rowptr + i); r.owner = i; r.deg = (int)(__ldg(P.rowptr + i + 1) - r.start);
-                    r.price = bid; r.pad = 0;
-                    *reinterpret_cast<int4 *>(P.rec + j) = *reinterpret_cast<const int4 *>(&r);
-                    P.rec[j].price = bid;
-                    P.price[j] = bid;
-                    P.p2o[i] = j;
-                    if (prev >= 0) P.p2o[prev] = -1; else ++myholes;
-                    P.list[a] = prev;                          // evicted owner takes the slot, or -1 = hole
-                    P.bidkey[j] = 0ull;
-                    if (tie) P.winpos[j] = 0x7fffffff;
-                }
-            }
-            if (tid == 0) s_red = 0;
-            __syncthreads();
-            if (myholes) atomicAdd(&s_red, myholes);
-            __syncthreads();
-            if (tid == 0) P.hole_count[blockIdx.x] = s_red;
-            if (gtid == 0) tp3 = sslapb_globaltimer();
-            GB();
-            if (gtid == 0) tp4 = sslapb_globaltimer();
-            // (3) push_all_left (:137-162): k-th hole left of new_nu <- k-th live entry right of it
-            if (warp == 0) {                                   // per-CTA hole counts -> total, my prefix, prefix of the split chunk
-                int ht = 0, hp = 0;
-                for (unsigned b = lane; b < nblk; b += 32) {
-                    const int h = P.hole_count[b];
-                    ht += h;
-                    if (b < blockIdx.x) hp += h;
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    ht += __shfl_xor_sync(SSLAPB_FULL, ht, off);
-                    hp += __shfl_xor_sync(SSLAPB_FULL, hp, off);
-                }
-                const int cb0 = (nu - ht) / L;
-                int h2 = 0;
-                for (int b = lane; b < cb0; b += 32) h2 += P.hole_count[b];
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) h2 += __shfl_xor_sync(SSLAPB_FULL, h2, off);
-                if (lane == 0) { s_hpre[0] = h2; s_hpre[1] = hp; s_hpre[2] = ht; s_red = 0; }
-            }
-            __syncthreads();
-            const int H = __shfl_sync(SSLAPB_FULL, s_hpre[2], 0), hpre = __shfl_sync(SSLAPB_FULL, s_hpre[1], 0);
-            const int new_nu = nu - H;
-            const int cb = new_nu / L;                         // chunk that contains the split point
-            int cnt = 0;
-            for (int a = cb * L + tid; a < new_nu; a += blockDim.x) cnt += (P.list[a] < 0);
-            if (cnt) atomicAdd(&s_red, cnt);
-            __syncthreads();
-            const int Hsplit = s_hpre[0] + s_red;              // holes in [0,new_nu)
-            __syncthreads();
-            int run = hpre;                                    // holes in [0, tile start)
-            for (int base = lo; base < hi; base += blockDim.x) {
-                const int a = base + tid;
-                int v = 0;
-                bool hole = false;
-                if (a < hi) { v = P.list[a]; hole = v < 0; }
-                int ttot;
-                const int before = run + block_excl_scan_flag(hole, ttot);
-                if (a < hi) {
-                    if (a < new_nu) {
-                        if (hole) P.list[a] = -(before + 2);   // rank-encoded; decoded by the next reader
-                    } else if (!hole) {
-                        P.mover[(a - new_nu) - (before - Hsplit)] = v;
-                    }
-                }
-                run += ttot;
-            }
-            if (gtid == 0) {
-                C->nu = new_nu;
-                C->its = its + 1;
-                C->tie_flag = 0;
-                C->rounds_grid += 1;
-                if (its + 1 >= max_iter) C->done = 3;
-                tp5 = sslapb_globaltimer();
+                if (gtid == 0) C->prof[6] += sslapb_globaltimer() - tc0;
             }
             GB();
-            if (gtid == 0) {
-                C->prof[0] += tp1 - tp0; C->prof[1] += tp3 - tp2; C->prof[2] += tp5 - tp4;
-                C->prof[7] += (tp2 - tp1) + (tp4 - tp3) + (sslapb_globaltimer() - tp5);
-            }
+#endif
         } else {
             // ================================ warp-list regimes: CTA 0 finishes the phase ================================
             if (blockIdx.x == 0) small_regime(P, C, nu, eps_f, its, max_iter, pmin, spread);
@@ -1066,14 +1124,57 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
     }
 }
 
-#ifdef SSLAPB_LONG_ROWS
-// only the cooperative launch: the state is initialised by sslapb_launch_auction (auction.cu)
-extern "C" cudaError_t sslapb_launch_auction_long(const SslapbAuctionParams *P, int grid, cudaStream_t stream)
+// Cooperative launch of this translation unit's kernel instance, in thread-block clusters of `cluster` CTAs when > 1.
+static cudaError_t launch_persistent(const SslapbAuctionParams *P, int grid, int cluster, cudaStream_t stream)
 {
     void *args[] = {(void *)P};
-    return cudaLaunchCooperativeKernel((const void *)sslapb_auction_kernel, dim3(grid), dim3(SSLAPB_THREADS), args, 0, stream);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(SSLAPB_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = cluster; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = cluster > 1 ? 2 : 1;
+    return cudaLaunchKernelExC(&cfg, (const void *)sslapb_auction_kernel, args);
+}
+#if defined(SSLAPB_LONG_ROWS)
+// (the state is initialised by sslapb_launch_auction, auction.cu)
+extern "C" cudaError_t sslapb_launch_auction_long(const SslapbAuctionParams *P, int grid, cudaStream_t stream)
+{
+    return launch_persistent(P, grid, 1, stream);
 }
 extern "C" int sslapb_coop_row_entries() { return 4 * SSLAPB_COOP_CHUNKS - 3; }
+#elif defined(SSLAPB_CLUSTER_REGIME)
+extern "C" cudaError_t sslapb_launch_auction_cluster(const SslapbAuctionParams *P, int grid, int cluster, cudaStream_t stream)
+{
+    return launch_persistent(P, grid, cluster, stream);
+}
+// Clusters of SSLAPB_CLUSTER CTAs, one CTA per SM: how many the device keeps co-resident (the grid is a multiple of the
+// cluster size: a B200 fits 17 clusters of 8 = 136 of its 148 SMs).  cluster = 1 when the device cannot do it.
+#define SSLAPB_CLUSTER 8
+extern "C" cudaError_t sslapb_auction_cluster_grid(int device, int *grid, int *cluster)
+{
+    int sms = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    *grid = sms;
+    *cluster = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sms / SSLAPB_CLUSTER * SSLAPB_CLUSTER); cfg.blockDim = dim3(SSLAPB_THREADS);
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = SSLAPB_CLUSTER; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, (const void *)sslapb_auction_kernel, &cfg) == cudaSuccess && ncl >= 2) {
+        const int g = min(ncl * SSLAPB_CLUSTER, sms / SSLAPB_CLUSTER * SSLAPB_CLUSTER);
+        if (g * 10 >= sms * 8) { *grid = g; *cluster = SSLAPB_CLUSTER; }     // not worth losing more than a fifth of the SMs
+    } else {
+        cudaGetLastError();
+    }
+    return cudaSuccess;
+}
 #else
 // ----------------------------------------------------------------------------------------------------------------------
 // Stand-alone bidding sweep (non-cooperative): the grid regime's step (1) for an explicit bidder list.  Used for
@@ -1142,13 +1243,15 @@ __global__ void sslapb_auction_init_kernel(SslapbAuctionParams P)
 }
 
 extern "C" cudaError_t sslapb_launch_auction_long(const SslapbAuctionParams *P, int grid, cudaStream_t stream);
-// long_rows: the longest row exceeds sslapb_coop_row_entries() entries -> the kernel instance of auction_long.cu
-extern "C" cudaError_t sslapb_launch_auction(const SslapbAuctionParams *P, int grid, int long_rows, cudaStream_t stream)
+extern "C" cudaError_t sslapb_launch_auction_cluster(const SslapbAuctionParams *P, int grid, int cluster, cudaStream_t stream);
+// Three instances of the persistent kernel: this one (lean), auction_long.cu (the longest row exceeds
+// sslapb_coop_row_entries() entries) and auction_cluster.cu (opt-in cluster regime, cluster > 1).
+extern "C" cudaError_t sslapb_launch_auction(const SslapbAuctionParams *P, int grid, int cluster, int long_rows, cudaStream_t stream)
 {
     sslapb_auction_init_kernel<<<grid, 1024, 0, stream>>>(*P);
     if (long_rows) return sslapb_launch_auction_long(P, grid, stream);
-    void *args[] = {(void *)P};
-    return cudaLaunchCooperativeKernel((const void *)sslapb_auction_kernel, dim3(grid), dim3(SSLAPB_THREADS), args, 0, stream);
+    if (cluster > 1) return sslapb_launch_auction_cluster(P, grid, cluster, stream);
+    return launch_persistent(P, grid, 1, stream);
 }
 
 extern "C" cudaError_t sslapb_auction_grid_size(int device, int *grid)

@@ -4,9 +4,13 @@
 
 // Control block in device memory: the only cross-CTA communication channel of the persistent kernel.
 struct SslapbCtrl {
+    // ---- line 0: the words the waiting CTAs poll (up to 147 CTAs, ~100 loads per microsecond on this one L2 line while
+    // CTA 0 or cluster 0 runs a phase alone) — nothing the working CTAs touch per round may share it
     unsigned bar_count;       // grid barrier: arrivals
     unsigned bar_gen;         // grid barrier: generation
     int abort_flag;           // set by the watchdog (a barrier waited longer than watchdog_ns) or an internal assert
+    int pad0[29];
+    // ---- line 1 onwards: round / phase state
     int nu;                   // number of unassigned persons (auction_.pyx:198 num_unassigned)
     int done;                 // 0 running | 1 target-eps CS holds (:275,309) | 2 eps < target (:280) | 3 max_iter (:309)
     float eps;                // current eps, float32 as in the reference (:180)
@@ -19,13 +23,14 @@ struct SslapbCtrl {
     int tie_flag;             // some atomicMax saw an equal bid this round -> run the position tie-break pass
     int ece_final;            // meta['eCE'] (:297); -1 until known
     long long rounds_grid, rounds_warp, rounds_solo;   // instrumentation: rounds executed per regime
+    long long rounds_cluster;                          // ... and by cluster 0 alone (mid-sized frontiers)
     unsigned long long pmin_key[2];                    // order-preserving image of a LOWER bound of every price (slot = phase & 1);
                                                        // prices never decrease, so a phase-start minimum stays valid all phase
     unsigned long long pmax_key;                       // running maximum of the prices (atomicMax by every winner): heuristic only
     long long prune_second_pass;                       // instrumentation: rows that needed the second (exactness) gather pass
     unsigned long long t_begin, t_end;                 // %globaltimer at kernel start / end
     unsigned long long prof[8];                        // ns spent (CTA 0 view): 0 grid bid, 1 grid tie+assign, 2 grid compaction,
-                                                       // 3 warp regime, 4 solo regime, 5 eCE/phase change, 6 epilogue, 7 barriers of the grid regime
+                                                       // 3 warp regime, 4 solo regime, 5 eCE/phase change, 6 cluster regime, 7 barriers of the grid regime
 };
 
 // Per-object record (32 B = one sector): everything a bidder needs to know about the object it wins, so that the
@@ -60,5 +65,7 @@ struct SslapbAuctionParams {
     double *chosen;           // per person: sum of (folded) values of entries equal to its object (get_obj, :504-521)
     SslapbCtrl *ctrl;
     int t_small;              // nu <= t_small (<= 32) -> CTA 0 runs the round alone (warp-list regime)
+    int t_cluster;            // t_small < nu <= t_cluster -> the CTAs of cluster 0 run the rounds (0: regime off)
+    int cluster;              // CTAs per cluster of the launch (1: no clusters)
     unsigned long long watchdog_ns;
 };

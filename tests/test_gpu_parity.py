@@ -398,6 +398,31 @@ def test_very_long_rows_use_the_cooperative_kernel_instance(gpu, oracle_mod):
             assert np.array_equal(prices_of(nat, h, mat.shape[1]), want["prices"]), name
 
 
+def test_cluster_regime_opt_in_bit_exact(gpu, oracle_mod):
+    """Opt-in regime ("t_cluster" > 0): the kernel is launched in thread-block clusters and cluster 0 alone runs the
+    rounds of mid-sized frontiers with hardware cluster barriers.  Same trajectory: sol, meta and prices bit-exact."""
+    sslap_b200, nat, h = gpu
+    cases = [(1000, 0.01, "int", 0), (4000, 0.01, "float", 1), (10000, 0.01, "float", 0), (300, 0.3, "float", 5)]
+    h.set_option("watchdog_ms", 20000)
+    try:
+        for (n, d, mode, seed) in cases:
+            loc, val = make_problem(n, d, mode, seed=seed)
+            want = oracle_mod.auction_solve(loc=loc, val=val, problem="max", return_prices=True, max_iter=60000)
+            for (t_small, t_cluster) in ((32, 512), (4, 64), (32, 100000)):
+                h.set_option("t_small", t_small)
+                h.set_option("t_cluster", t_cluster)
+                got = sslap_b200.auction_solve(loc=loc, val=val, size=(n, n), problem="max", cardinality_check=False,
+                                               max_iter=60000, _raw_meta=True)
+                assert got["raw"].rounds_cluster > 0
+                assert np.array_equal(got["sol"], want["sol"]), (n, t_small, t_cluster)
+                assert_meta_equal(got["meta"], want["meta"])
+                assert np.array_equal(prices_of(nat, h, n), want["prices"])
+    finally:
+        h.set_option("t_small", 32)
+        h.set_option("t_cluster", 0)
+        h.set_option("watchdog_ms", 120000)
+
+
 def test_randomized_differential_against_the_oracle(gpu, oracle_mod):
     """120 seeded random instances across shapes, densities, cost kinds, objectives, eps options, iteration caps and
     regime splits: `sol` and the integer meta keys must equal the oracle's bit for bit; so must the float64 prices."""
