@@ -113,6 +113,25 @@ def reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic_bytes():
+    """DRAM bytes of ONE launch of the roofline kernel on this workload, from the committed ncu capture (never measured
+    under the profiler inside a bench run); None when the capture is missing."""
+    import csv
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_bid_sweep_full_raw_final.csv")
+    try:
+        with open(path, newline="") as f:
+            rows = list(csv.reader(f))
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(key)
+            tot += float(vals[i].replace(",", "")) * scale[units[i]]
+        return int(tot)
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -240,7 +259,9 @@ def main():
             "gpu_launches": 4 * args.steps,          # per step: coo_ingest, rowmax, auction_init, persistent auction kernel
             "roofline": {"kernel": "sslapb_bid_sweep_kernel (full frontier, N bidders, merge atomics on)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "bytes_per_launch": sweep_bytes, "avg_launch_us": avg.value * 1e3,
+                         "traffic": ncu_traffic_bytes(), "traffic_source": "profiles/r1_bid_sweep_full_raw_final.csv "
+                         "(ncu --set full of this launch: dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "bytes_per_launch": sweep_bytes, "avg_launch_us": avg.value * 1e3,
                          "note": "the whole solve is round-latency bound (see device_ms / DESIGN.md); this is the CSR traversal"},
             "clocks": sampler.summary(),
         }
