@@ -289,6 +289,8 @@ __device__ __forceinline__ int chain_rounds(const SslapbAuctionParams &P, double
 // person — it lost — or the owner it evicted, whose row was requested during the sweep), publishes (object, bid), and
 // after one barrier decides by itself whether it won (no serial merge); winners commit; after a second barrier every
 // warp derives the compacted list (push_all_left, auction_.pyx:137-162) redundantly from shared memory.
+struct SslapbDuoPub { double bid; long long pstart, st; int j, powner, pdeg, me, dg, pad; };   // 48 B, see the duo rounds
+
 #ifdef SSLAPB_LONG_ROWS
 // Very long rows (more than 8 warp passes; only in the kernel instance built with SSLAPB_LONG_ROWS, auction_long.cu): the
 // warp that owns such a bidder does not sweep it alone.  It flags the row as pending; the round's first barrier carries
@@ -318,7 +320,11 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
         single = (((st + dg + 3) >> 2) - (st >> 2)) <= 32;
         cur = sslapb_load_chunk(P.cols, P.vals, (st >> 2) + lane, single && ((st >> 2) + lane < ((st + dg + 3) >> 2)));
     }
+#ifdef SSLAPB_LONG_ROWS
     while (nu > 1 && nu <= SSLAPB_THREADS / 32 && !done) {
+#else
+    while (nu > 2 && nu <= SSLAPB_THREADS / 32 && !done) {     // two bidders: duo rounds below
+#endif
         SslapbBid B;
         B.j = -1; B.bid = 0.0; B.powner = -1; B.pdeg = 0; B.pstart = 0;
         SslapbChunk nxt = cur;
@@ -401,6 +407,62 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
         }
         // no third barrier: s_list / s_j are rewritten only after the next round's first barrier / after this round's second
     }
+#ifndef SSLAPB_LONG_ROWS
+    // ---- exactly two bidders (45 % of the few-bidder rounds at C3): warps 0 and 1 alone, ONE named barrier per round.
+    // Each publishes its bid together with its own list entry and the record of the object's owner; after the barrier
+    // both warps derive the whole outcome from the two publications (who wins a contested object: higher bid, position
+    // 0 on a tie, :379; whose slot turns into a hole; push_all_left for two positions) — no second barrier, no list in
+    // shared memory, the other 14 warps wait at the caller's block barrier.  The publications are double-buffered: a warp
+    // can be at most one round ahead of the other.
+    if (nu == 2 && !done && a < 2) {
+        __shared__ SslapbDuoPub s_duo[2][2];
+        int par = 0;
+        while (nu == 2 && !done) {
+            SslapbBid B;
+            B.j = -1; B.bid = 0.0; B.powner = -1; B.pdeg = 0; B.pstart = 0;
+            SslapbChunk nxt = cur;
+            bool nsingle = false;
+            bool ok = single;
+            if (ok) ok = sweep_single(P, cur, st, dg, eps, true, B, nxt, nsingle);
+            if (!ok) {                                         // long row (bound-pruned), or every candidate at -inf (exact, unpruned)
+                B = row_bid_rec<32>(P.cols, P.vals, P.rec, st, st + dg, lane, eps, s_bounds[0],
+                                    single ? SSLAPB_NEG_INF : __ldg(P.rowmax + me) - s_bounds[1]);
+                ok = B.j >= 0;
+                const long long n0 = B.pstart >> 2, n1 = (B.pstart + B.pdeg + 3) >> 2;
+                nsingle = (n1 - n0) <= 32;
+                nxt = sslapb_load_chunk(P.cols, P.vals, n0 + lane, ok && B.powner >= 0 && nsingle && (n0 + lane < n1));
+            }
+            if (!ok) B.j = -1;
+            if (lane == 0) {
+                SslapbDuoPub pb;
+                pb.bid = B.bid; pb.pstart = B.pstart; pb.st = st; pb.j = B.j; pb.powner = B.powner; pb.pdeg = B.pdeg;
+                pb.me = me; pb.dg = dg; pb.pad = 0;
+                s_duo[par][a] = pb;
+            }
+            asm volatile("bar.sync 1, 64;" ::: "memory");
+            const SslapbDuoPub O = s_duo[par][a ^ 1];
+            par ^= 1;
+            if (B.j < 0 || O.j < 0) { done = 4; break; }       // empty row: rejected at CSR build, cannot happen
+            const bool contested = O.j == B.j;
+            const bool won = !contested || B.bid > O.bid || (B.bid == O.bid && a == 0);
+            const bool owon = !contested || !won;
+            if (won && lane == 0) commit_win(P, me, st, dg, B);
+            // next occupant of my slot / of the other slot (-1 = hole)
+            const int nme = won ? B.powner : me, ome = owon ? O.powner : O.me;
+            ++its; ++rounds;
+            if (its >= max_iter) done = 3;
+            if (nme >= 0 && ome >= 0) {                        // both slots stay live
+                if (won) { me = B.powner; st = B.pstart; dg = B.pdeg; cur = nxt; single = nsingle; }
+                continue;                                      // lost: same person, same row, still in registers
+            }
+            // push_all_left (:137-162) for two positions: the survivor, if any, ends up at position 0 = warp 0
+            nu = (nme >= 0) + (ome >= 0);
+            if (nme >= 0) { if (won) { me = B.powner; st = B.pstart; dg = B.pdeg; } }
+            else if (ome >= 0) { me = ome; st = owon ? O.pstart : O.st; dg = owon ? O.pdeg : O.dg; }
+            else me = -1;
+        }
+    }
+#endif
     return nu;
 }
 
