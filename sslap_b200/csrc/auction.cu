@@ -322,9 +322,6 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
     }
 #ifdef SSLAPB_LONG_ROWS
     while (nu > 1 && nu <= SSLAPB_THREADS / 32 && !done) {
-#else
-    while (nu > 2 && nu <= SSLAPB_THREADS / 32 && !done) {     // two bidders: duo rounds below
-#endif
         SslapbBid B;
         B.j = -1; B.bid = 0.0; B.powner = -1; B.pdeg = 0; B.pstart = 0;
         SslapbChunk nxt = cur;
@@ -407,6 +404,86 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
         }
         // no third barrier: s_list / s_j are rewritten only after the next round's first barrier / after this round's second
     }
+#else
+    // ---- 3..16 bidders, ONE named barrier per round among the active warps only.  Every active warp publishes its bid
+    // together with its list entry and the record of the object's owner; after the barrier lane b of EVERY active warp
+    // holds publication b and the whole outcome is derived redundantly, in registers: who is beaten (:375-385: a higher
+    // bid on the same object, or an equal one from an earlier position), the next occupant of every position (evicted
+    // owner, the loser itself, or a hole, :401-413), the compaction (push_all_left, :137-162).  Winners commit; a warp whose
+    // position falls off the end leaves for the caller's block barrier.  Publications are double-buffered (a warp can
+    // be at most one round ahead).
+    __shared__ SslapbDuoPub s_pub[2][SSLAPB_THREADS / 32];
+    int par = 0;
+    while (active && nu > 2 && !done) {
+        SslapbBid B;
+        B.j = -1; B.bid = 0.0; B.powner = -1; B.pdeg = 0; B.pstart = 0;
+        SslapbChunk nxt = cur;
+        bool nsingle = false;
+        bool ok = single;
+        if (ok) ok = sweep_single(P, cur, st, dg, eps, true, B, nxt, nsingle);
+        if (!ok) {                                             // long row (bound-pruned), or every candidate at -inf (exact, unpruned)
+            B = row_bid_rec<32>(P.cols, P.vals, P.rec, st, st + dg, lane, eps, s_bounds[0],
+                                single ? SSLAPB_NEG_INF : __ldg(P.rowmax + me) - s_bounds[1]);
+            ok = B.j >= 0;
+            const long long n0 = B.pstart >> 2, n1 = (B.pstart + B.pdeg + 3) >> 2;
+            nsingle = (n1 - n0) <= 32;
+            nxt = sslapb_load_chunk(P.cols, P.vals, n0 + lane, ok && B.powner >= 0 && nsingle && (n0 + lane < n1));
+        }
+        if (!ok) B.j = -1;
+        if (lane == 0) {
+            SslapbDuoPub pb;
+            pb.bid = B.bid; pb.pstart = B.pstart; pb.st = st; pb.j = B.j; pb.powner = B.powner; pb.pdeg = B.pdeg;
+            pb.me = me; pb.dg = dg; pb.pad = 0;
+            s_pub[par][a] = pb;
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(nu * 32) : "memory");
+        SslapbDuoPub O;
+        O.bid = 0.0; O.pstart = 0; O.st = 0; O.j = -1 - lane; O.powner = -1; O.pdeg = 0; O.me = -1; O.dg = 0; O.pad = 0;
+        if (lane < nu) O = s_pub[par][lane];
+        par ^= 1;
+        if (__any_sync(SSLAPB_FULL, lane < nu && O.j < 0)) { done = 4; break; }   // empty row: rejected at CSR build
+        bool beaten = false;
+        for (int c = 0; c < nu; ++c) {
+            const int cj = __shfl_sync(SSLAPB_FULL, O.j, c);
+            const double cb = __shfl_sync(SSLAPB_FULL, O.bid, c);
+            beaten |= (c != lane) && (cj == O.j) && (cb > O.bid || (cb == O.bid && c < lane));
+        }
+        const bool wonb = (lane < nu) && !beaten;              // position `lane` wins its object
+        const int nme_b = wonb ? O.powner : O.me;              // next occupant of position `lane`; -1 = hole
+        const long long nst_b = wonb ? O.pstart : O.st;
+        const int ndg_b = wonb ? O.pdeg : O.dg;
+        const bool won = __shfl_sync(SSLAPB_FULL, (int)wonb, a) != 0;
+        if (won && lane == 0) commit_win(P, me, st, dg, B);
+        ++its; ++rounds;
+        if (its >= max_iter) done = 3;
+        // compaction (:429-430): the k-th hole left of the new count takes the k-th live entry right of it
+        const unsigned holes = __ballot_sync(SSLAPB_FULL, lane < nu && nme_b < 0);
+        const int new_nu = nu - __popc(holes);
+        int src = a;
+        if (holes) {
+            const unsigned valid = (1u << nu) - 1u, leftm = (1u << new_nu) - 1u;
+            const unsigned left_holes = holes & leftm, right_live = valid & ~holes & ~leftm;
+            if (a < new_nu && ((left_holes >> a) & 1u)) {
+                unsigned m = right_live;
+                for (int q = __popc(left_holes & ((1u << a) - 1u)); q > 0; --q) m &= m - 1u;
+                src = __ffs(m) - 1;
+            }
+        }
+        const int e_me = __shfl_sync(SSLAPB_FULL, nme_b, src);
+        const long long e_st = __shfl_sync(SSLAPB_FULL, nst_b, src);
+        const int e_dg = __shfl_sync(SSLAPB_FULL, ndg_b, src);
+        nu = new_nu;
+        active = a < nu;
+        if (!active) { me = -1; break; }                       // my position fell off the end
+        me = e_me; st = e_st; dg = e_dg;
+        if (src == a && won) { cur = nxt; single = nsingle; }  // the evicted owner: row already requested
+        else if (src == a) { /* lost: same person, same row, still in registers */ }
+        else {
+            single = (((st + dg + 3) >> 2) - (st >> 2)) <= 32;
+            cur = sslapb_load_chunk(P.cols, P.vals, (st >> 2) + lane, single && ((st >> 2) + lane < ((st + dg + 3) >> 2)));
+        }
+    }
+#endif
 #ifndef SSLAPB_LONG_ROWS
     // ---- exactly two bidders (45 % of the few-bidder rounds at C3): warps 0 and 1 alone, ONE named barrier per round.
     // Each publishes its bid together with its own list entry and the record of the object's owner; after the barrier
