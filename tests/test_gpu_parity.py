@@ -423,6 +423,41 @@ def test_cluster_regime_opt_in_bit_exact(gpu, oracle_mod):
         h.set_option("watchdog_ms", 120000)
 
 
+def test_two_handles_in_two_threads_and_option_validation(gpu, oracle_mod):
+    """One handle = one stream + its own scratch; distinct handles may be driven from different threads (the persistent
+    cooperative kernels of the two solves simply take turns on the device).  Options reject bad values."""
+    import threading
+    sslap_b200, nat, h = gpu
+    for name, value in (("t_small", 33), ("t_small", -1), ("t_cluster", -5), ("watchdog_ms", 0), ("no_such_option", 1)):
+        with pytest.raises(ValueError):
+            h.set_option(name, value)
+    problems = [make_problem(n, d, "float", seed=s) for (n, d, s) in ((1500, 0.01, 1), (900, 0.03, 2), (2500, 0.004, 3))]
+    wants = [oracle_mod.auction_solve(loc=l, val=v, problem="max") for (l, v) in problems]
+    results, errors = {}, []
+
+    def work(tid):
+        try:
+            hh = nat.Handle(0)
+            for rep in range(4):
+                for k, (l, v) in enumerate(problems):
+                    n = int(l[:, 0].max()) + 1
+                    results[(tid, rep, k)] = sslap_b200.auction_solve(loc=l, val=v, size=(n, n), problem="max",
+                                                                      cardinality_check=bool(rep % 2), _handle=hh)
+        except Exception as e:                                   # pragma: no cover
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert len(results) == 2 * 4 * len(problems)
+    for (tid, rep, k), got in results.items():
+        assert np.array_equal(got["sol"], wants[k]["sol"])
+        assert_meta_equal(got["meta"], wants[k]["meta"])
+
+
 def test_randomized_differential_against_the_oracle(gpu, oracle_mod):
     """120 seeded random instances across shapes, densities, cost kinds, objectives, eps options, iteration caps and
     regime splits: `sol` and the integer meta keys must equal the oracle's bit for bit; so must the float64 prices."""
