@@ -434,7 +434,15 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
     CK(cudaMemcpyAsync(chosen.data(), P.chosen, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&c, P.ctrl, sizeof c, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (c.abort_flag) return fail(h, SSLAPB_E_ABORTED, c.abort_flag == 2 ? "empty row reached the bidding kernel" : "device watchdog fired");
+    if (c.abort_flag) {
+        std::string msg = c.abort_flag == 2 ? "empty row reached the bidding kernel" : "device watchdog fired";
+        if (P.cluster > 1) {                                   // where the CTAs of cluster 0 were (barrier count per CTA)
+            msg += " [nu=" + std::to_string(c.nu) + " its=" + std::to_string(c.its) + " cluster barriers:";
+            for (int k = 0; k < P.cluster && k < 16; ++k) msg += " " + std::to_string(c.dbg[k]);
+            msg += "]";
+        }
+        return fail(h, SSLAPB_E_ABORTED, msg);
+    }
     double obj = 0.0;                                          // get_obj, auction_.pyx:489-523 (row order, double)
     long long assigned = 0;
     for (int i = 0; i < N; ++i) {

@@ -919,6 +919,7 @@ __device__ __forceinline__ int block_excl_scan_flag(bool flag, int &total)
 // One Jacobi round with the bidders spread over several CTAs (auction_.pyx:337-430) — by the whole grid (grid barriers) or,
 // for mid-sized frontiers, by the CTAs of cluster 0 alone (hardware cluster barriers, ~0.25 us instead of ~1.5 us each;
 // the other CTAs wait at one grid barrier for the cluster to hand the phase over).
+__shared__ unsigned ss_cbar;                                   // cluster barriers this CTA has arrived at (zeroed by the kernel)
 struct SslapbScope { int blk, nblk, gwarp, nwarps; bool lead; };   // CTA rank / count, warp rank / count, the one reporting thread
 template <bool CLUSTER>
 __device__ __forceinline__ bool round_barrier(SslapbCtrl *C, unsigned nblk, unsigned &epoch, unsigned long long watchdog_ns)
@@ -927,6 +928,7 @@ __device__ __forceinline__ bool round_barrier(SslapbCtrl *C, unsigned nblk, unsi
         // block barrier first (every warp converged, CTA-local hazards closed), then the hardware cluster barrier in its
         // non-.aligned form: an opaque asm gives the compiler no reason to reconverge a warp in front of it
         __syncthreads();
+        if (threadIdx.x == 0) *(volatile unsigned *)&C->dbg[blockIdx.x & 15] = ++ss_cbar;   // progress marker (watchdog report)
         asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
         return true;
     }
@@ -1108,6 +1110,9 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
     unsigned bar_epoch = 0;                                    // barriers passed so far * #CTAs (wraps harmlessly)
 
     if (gtid == 0) C->t_begin = sslapb_globaltimer();
+#ifdef SSLAPB_CLUSTER_REGIME
+    if (tid == 0) ss_cbar = 0;
+#endif
 
     for (;;) {
         // ---- loop top: every CTA arrives here right after a grid barrier; the control block is stable.  ONE thread per

@@ -29,6 +29,8 @@ struct SslapbCtrl {
     unsigned long long pmax_key;                       // running maximum of the prices (atomicMax by every winner): heuristic only
     long long prune_second_pass;                       // instrumentation: rows that needed the second (exactness) gather pass
     unsigned long long t_begin, t_end;                 // %globaltimer at kernel start / end
+    unsigned dbg[16];                                  // cluster regime: last barrier each CTA of cluster 0 arrived at
+                                                       // ((round << 3) | barrier index), reported when the watchdog fires
     unsigned long long prof[8];                        // ns spent (CTA 0 view): 0 grid bid, 1 grid tie+assign, 2 grid compaction,
                                                        // 3 warp regime, 4 solo regime, 5 eCE/phase change, 6 cluster regime, 7 barriers of the grid regime
 };
