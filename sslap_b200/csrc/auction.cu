@@ -10,11 +10,19 @@
 //     winners leave holes (:411-413), and push_all_left (:137-162) fills the k-th hole left of the new count with the
 //     k-th live entry right of it.  All of that is order-independent per round, hence data-parallel.
 //
-// Three regimes, chosen by the frontier size nu (monotone non-increasing inside an eps-phase):
-//   grid  (nu > t_small): all CTAs; warp per bidder; 64-bit atomicMax of the order-preserving bid per object (+ an
-//                         atomicMin of the list position only in rounds where an equal bid was seen); 3 grid barriers.
-//   warp  (4 < nu <= 32): CTA 0 only; warp w sweeps the row of list position w; warp 0 merges through shuffles.
-//   solo  (nu <= 4)     : warp 0 of CTA 0 only; 32/16/8 lanes per bidder; no block barrier at all.
+// Regimes, chosen by the frontier size nu (monotone non-increasing inside an eps-phase):
+//   grid      (nu > t_small = 32): all CTAs; warp per bidder; 64-bit atomicMax of the order-preserving bid per object
+//                                  (+ an atomicMin of the list position only in rounds where an equal bid was seen);
+//                                  3 grid barriers (spread_round<false>).
+//   cluster   (opt-in, t_small < nu <= t_cluster): the same round run by the 8 CTAs of cluster 0 with hardware cluster
+//                                  barriers (spread_round<true>; instance of auction_cluster.cu).
+//   17..32    CTA 0 only; list positions strided over its 16 warps, warp 0 merges through shuffles (warp_resolve).
+//   3..16     CTA 0 only; warp a owns position a; ONE named barrier per round, outcome derived redundantly in registers
+//             (multi_rounds; the instance of auction_long.cu keeps a two-barrier form with a whole-CTA sweep of very
+//             long rows).
+//   2         warps 0 and 1 of CTA 0 (duo rounds inside multi_rounds).
+//   1         warp 0 of CTA 0, no barrier at all (chain_rounds; coop_chain_rounds when the row is long).
+// This file is compiled three times (plain, SSLAPB_LONG_ROWS, SSLAPB_CLUSTER_REGIME): see the two wrapper units.
 #include "auction.cuh"
 
 #define SSLAPB_THREADS 512       // persistent kernel: one CTA of 16 warps per SM (128 registers per thread)
