@@ -418,8 +418,10 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
     // holds publication b and the whole outcome is derived redundantly, in registers: who is beaten (:375-385: a higher
     // bid on the same object, or an equal one from an earlier position), the next occupant of every position (evicted
     // owner, the loser itself, or a hole, :401-413), the compaction (push_all_left, :137-162).  Winners commit; a warp whose
-    // position falls off the end leaves for the caller's block barrier.  Publications are double-buffered (a warp can
-    // be at most one round ahead).
+    // position falls off the end leaves for the caller's block barrier.  Publications are double-buffered: among the
+    // warps that stay a warp can be at most one round ahead; a warp that leaves after round r has taken its only look at
+    // round r's buffer with the first instruction after the barrier, two full rounds (thousands of cycles) before any
+    // stayer can write that buffer again.
     __shared__ SslapbDuoPub s_pub[2][SSLAPB_THREADS / 32];
     int par = 0;
     while (active && nu > 2 && !done) {
