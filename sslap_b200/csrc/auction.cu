@@ -418,12 +418,11 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
     // holds publication b and the whole outcome is derived redundantly, in registers: who is beaten (:375-385: a higher
     // bid on the same object, or an equal one from an earlier position), the next occupant of every position (evicted
     // owner, the loser itself, or a hole, :401-413), the compaction (push_all_left, :137-162).  Winners commit; a warp whose
-    // position falls off the end leaves for the caller's block barrier.  Publications are double-buffered: among the
-    // warps that stay a warp can be at most one round ahead; a warp that leaves after round r has taken its only look at
-    // round r's buffer with the first instruction after the barrier, two full rounds (thousands of cycles) before any
-    // stayer can write that buffer again.
+    // position falls off the end leaves for the caller's block barrier.  Publications are double-buffered: a warp can be
+    // at most one round ahead of any warp that took part in the previous round (leavers included, see below).
     __shared__ SslapbDuoPub s_pub[2][SSLAPB_THREADS / 32];
     int par = 0;
+    int bar_warps = nu;                                        // warps expected at the next named barrier
     while (active && nu > 2 && !done) {
         SslapbBid B;
         B.j = -1; B.bid = 0.0; B.powner = -1; B.pdeg = 0; B.pstart = 0;
@@ -446,7 +445,7 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
             pb.me = me; pb.dg = dg; pb.pad = 0;
             s_pub[par][a] = pb;
         }
-        asm volatile("bar.sync 1, %0;" ::"r"(nu * 32) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"r"(bar_warps * 32) : "memory");
         SslapbDuoPub O;
         O.bid = 0.0; O.pstart = 0; O.st = 0; O.j = -1 - lane; O.powner = -1; O.pdeg = 0; O.me = -1; O.dg = 0; O.pad = 0;
         if (lane < nu) O = s_pub[par][lane];
@@ -482,9 +481,16 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
         const int e_me = __shfl_sync(SSLAPB_FULL, nme_b, src);
         const long long e_st = __shfl_sync(SSLAPB_FULL, nst_b, src);
         const int e_dg = __shfl_sync(SSLAPB_FULL, ndg_b, src);
+        // the NEXT barrier still counts this round's leavers: they arrive (without waiting) only after their look at
+        // this round's buffer above, so no stayer can get two rounds ahead and overwrite it under them
+        bar_warps = nu;
         nu = new_nu;
         active = a < nu;
-        if (!active) { me = -1; break; }                       // my position fell off the end
+        if (!active) {                                         // my position fell off the end
+            if (nu > 2 && !done) asm volatile("bar.arrive 1, %0;" ::"r"(bar_warps * 32) : "memory");
+            me = -1;
+            break;
+        }
         me = e_me; st = e_st; dg = e_dg;
         if (src == a && won) { cur = nxt; single = nsingle; }  // the evicted owner: row already requested
         else if (src == a) { /* lost: same person, same row, still in registers */ }
