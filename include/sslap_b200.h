@@ -74,7 +74,7 @@ void sslapb_destroy(sslapb_handle *h);
 const char *sslapb_last_error(const sslapb_handle *h);
 /* tuning knobs: "t_small" (frontier size at or below which CTA 0 runs rounds alone, 0..32), "t_cluster" (frontier size
    at or below which one thread-block cluster of 8 CTAs runs the rounds with hardware cluster barriers; 0 = off, the
-   default — opt-in), "watchdog_ms" (device watchdog of a single barrier wait, default 120000) */
+   default — opt-in, honoured only while t_small is 32), "watchdog_ms" (device watchdog of a single barrier wait, default 120000) */
 int  sslapb_set_option(sslapb_handle *h, const char *name, int64_t value);
 
 /* Pinned host memory for callers that want asynchronous staging (bench.py's e2e leg). */
