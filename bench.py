@@ -1,16 +1,22 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the sslap auction hot path on B200 (contract: see DESIGN.md §Measurement).
+"""bench.py — headline benchmark of the sslap auction hot path on B200 (contract: see DESIGN.md §5).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A "step" is ONE full auction_solve of BASELINE.json configs[2]: a random 100k x 100k cost matrix at 0.1 % density
-(~10.09 M nnz, float costs U(0,100), planted feasible), problem='min', cardinality_check=False.
-  value   = nnz / (device-resident solve time)   [edges/s]; COO already in HBM, timed region = CSR build + solve + D2H of sol
-  e2e     = same metric through the public Python API (sslap_b200.auction_solve) with HOST (pinned) buffers
-  roofline= the full-frontier bidding sweep kernel (the CSR traversal the north star names), CUDA-event timed, L2 flushed
+A "step" is ONE full auction_solve of BASELINE.json configs[2] (the config the metric is quoted on): a random
+100k x 100k cost matrix at 0.1 % density (~10.09 M nnz, float costs U(0,100), planted feasible), problem='min',
+cardinality_check=False.
+  value    = nnz / (solve time with the COO already in HBM)  [edges/s]; timed region = CSR build + solve + D2H of sol
+  e2e      = the same metric through the public Python API (sslap_b200.auction_solve) with HOST (pinned) buffers;
+             e2e_pageable = the literal drop-in call (plain numpy arrays, default handle)
+  roofline = the full-frontier bidding sweep kernel (the CSR traversal the north star names), CUDA-event timed on the
+             handle's stream, L2 flushed before every launch; `insitu` = the same step timed inside the persistent kernel
   cpu_baseline = the unmodified reference (oracle/_ref) on ONE host core, one full solve of the same instance
-With N > 1 (torchrun) every rank solves its own copy of the instance: the path has no cross-GPU exchange for
-independent problems ("replicas only", weak scaling: equal work per rank); times are max over ranks.
+With N > 1 (torchrun, one process per GPU) the ranks solve the SAME single problem together: persons are row-sharded,
+the bidding step of the large-frontier rounds is split over the GPUs and the bids are exchanged in-kernel over NVLink
+(strong scaling); the line also carries `c5_batch` — BASELINE.json configs[4], 4096 independent 512 x 512
+problems dealt out to the ranks (problems/s) — and, at N = 8, `c4` (configs[3], N = 1M with the Hopcroft-Karp check).
+Times are device/wall maxima over the ranks.
 """
 import argparse
 import ctypes as C
@@ -29,6 +35,15 @@ sys.path.insert(0, ROOT)
 N_ROWS = 100000
 DENSITY = 0.001
 WORKLOAD = "C3: random 100k x 100k, 0.1% density (~10.09M nnz), float costs U(0,100), min, cardinality_check=False"
+C5_PROBLEMS, C5_N, C5_DENSITY = 4096, 512, 0.05
+
+
+def make_config(nnz, world):
+    """Identical in both arms (the driver compares the dicts)."""
+    return {"workload": WORKLOAD, "n": N_ROWS, "nnz": int(nnz), "seed": 0,
+            "parallelism": "single GPU" if world == 1 else f"one problem, persons row-sharded x{world} (NVLink bid exchange)",
+            "l2": "inputs (162 MB COO + 121 MB CSR per step) exceed the 126 MB L2; the sweep leg flushes L2 explicitly "
+                  "(256 MB memset) before every launch"}
 
 
 def measured_peaks():
@@ -92,19 +107,29 @@ def reference_arm(args, rank, world):
             t = time.perf_counter()
             r = oracle.auction_solve(loc=loc, val=val, problem="min", faithful_scan=True)
             return time.perf_counter() - t, r
-    # one solve is ~20 s of single-core work: bound the run to a few minutes whatever K/W the driver passes
+    # One step = one full solve (~9-20 s of single-core work).  --warmup / --steps are honoured as given unless the whole
+    # run would exceed ~5 minutes; then the counts are cut (steps first) and the line reports what actually ran.
     t_first, r = solve()
-    budget = 240.0
-    steps = max(1, min(args.steps, int(budget / max(t_first, 1e-3)) - 1))
-    times = [solve()[0] for _ in range(steps)] if args.warmup > 0 else [t_first] + [solve()[0] for _ in range(steps - 1)]
+    budget = 300.0
+    afford = max(1, int(budget / max(t_first, 1e-3)))          # solves we can afford in total (the first one included)
+    warm = min(max(args.warmup, 0), max(afford - 1, 0))
+    steps = max(1, min(args.steps, afford - warm))
+    times = []
+    if warm == 0:
+        times.append(t_first)                                   # no warm-up asked for (or affordable): the first solve counts
+    else:
+        for _ in range(warm - 1):
+            solve()
+    while len(times) < steps:
+        times.append(solve()[0])
     ms = 1e3 * sum(times) / len(times)
     value = nnz / (ms * 1e-3)
     line = {
         "impl": "reference", "metric": "auction_solve_edges_per_s", "value": value, "unit": "edges/s", "n_gpus": args.gpus,
-        "steps": len(times), "warmup": 1 if args.warmup > 0 else 0, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n": N_ROWS, "nnz": nnz, "seed": 0},
-        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": 1, "kind": kind,
+        "steps": len(times), "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": make_config(nnz, world),
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": 1, "kind": kind, "host_cores": os.cpu_count(),
                          "sample": f"{len(times)} full solve(s) of the same C3 instance, single thread (the reference has no threads); "
                                    f"its={r['meta']['its']}"},
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -117,19 +142,21 @@ def ncu_traffic_bytes():
     """DRAM bytes of ONE launch of the roofline kernel on this workload, from the committed ncu capture (never measured
     under the profiler inside a bench run); None when the capture is missing."""
     import csv
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_bid_sweep_full_raw_final.csv")
-    try:
-        with open(path, newline="") as f:
-            rows = list(csv.reader(f))
-        hdr, units, vals = rows[0], rows[1], rows[2]
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        tot = 0.0
-        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            i = hdr.index(key)
-            tot += float(vals[i].replace(",", "")) * scale[units[i]]
-        return int(tot)
-    except Exception:
-        return None
+    for name in ("r2_bid_sweep_full_raw.csv", "r1_bid_sweep_full_raw_final.csv"):
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            with open(path, newline="") as f:
+                rows = list(csv.reader(f))
+            hdr, units, vals = rows[0], rows[1], rows[2]
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            tot = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = hdr.index(key)
+                tot += float(vals[i].replace(",", "")) * scale[units[i]]
+            return int(tot), "profiles/" + name
+        except Exception:
+            continue
+    return None, None
 
 
 def main():
@@ -139,6 +166,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the configs[4] batch block")
+    ap.add_argument("--c4", choices=["auto", "on", "off"], default="auto", help="configs[3] block (auto: only at 8 GPUs)")
+    ap.add_argument("--t-shard", type=int, default=None, help="override option t_shard of the row-sharded solve")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -157,12 +187,17 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import sslap_b200
-    from sslap_b200 import _native as nat
+    from sslap_b200 import _native as nat, parallel
     from sslap_b200.datagen import make_problem, objective
     L = nat.load()
-    h = nat.Handle(local)
+    h = nat.default_handle(local)                                          # the handle the drop-in call uses
+    if world > 1:
+        parallel.init_row_sharding(h, 1 << 20)                             # communicator of the row-sharded solve
+        if args.t_shard is not None:
+            h.set_option("t_shard", args.t_shard)
+    warmup = max(args.warmup, 3)
 
-    loc, val = make_problem(N_ROWS, DENSITY, "float", seed=0)             # every rank solves its own copy of the same instance
+    loc, val = make_problem(N_ROWS, DENSITY, "float", seed=0)             # every rank holds the (same) full problem
     nnz = int(val.size)
 
     def barrier():
@@ -170,6 +205,12 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # ---------------- leg 1: inputs resident in HBM ----------------
     d_loc = torch.from_numpy(loc).cuda()
@@ -183,94 +224,152 @@ def main():
         if rc != 0:
             raise RuntimeError(f"sslapb_auction_coo -> {rc}: {h.last_error()}")
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         step_resident()
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    solve_ms, setup_ms = [], []
-    t0 = time.perf_counter()
+    solve_ms, setup_ms, xchg_ms, sharded_ms, insitu_us = [], [], [], [], []
     for _ in range(args.steps):
         step_resident()                                                    # synchronous: returns after the D2H of sol
         solve_ms.append(meta.solve_ms); setup_ms.append(meta.setup_ms)
+        xchg_ms.append(meta.xchg_ms); sharded_ms.append(meta.sharded_ms); insitu_us.append(meta.sweep_insitu_us)
     ev1.record()
     barrier()
-    wall = time.perf_counter() - t0
-    dev_ms = ev0.elapsed_time(ev1)
-    t_res = torch.tensor([max(dev_ms, 0.0) / args.steps], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
-    ms_step = float(t_res.item())
+    ms_step = max_over_ranks(max(ev0.elapsed_time(ev1), 0.0) / args.steps)
     its, obj = int(meta.its), objective(loc, val, sol)
     assert sorted(sol.tolist()) == list(range(N_ROWS)) and meta.soln_found == 1, "bench solve did not produce a perfect optimal matching"
+    rounds_sharded, row_range = int(meta.rounds_sharded), (int(meta.row_lo), int(meta.row_hi))
+    launches_per_step = 4 + (1 if world > 1 else 0)   # coo_ingest, rowmax, auction_init, persistent kernel (+ row_split)
 
-    # ---------------- leg 2: end to end through the public API, host (pinned) buffers ----------------
+    # ---------------- leg 2: end to end through the public API, host buffers ----------------
     p_loc = L.sslapb_host_alloc(loc.nbytes)
     p_val = L.sslapb_host_alloc(val.nbytes)
     h_loc = np.frombuffer((C.c_char * loc.nbytes).from_address(p_loc), dtype=np.int32).reshape(loc.shape)
     h_val = np.frombuffer((C.c_char * val.nbytes).from_address(p_val), dtype=np.float64)
     h_loc[:] = loc
     h_val[:] = val
-    for _ in range(2):
-        sslap_b200.auction_solve(loc=h_loc, val=h_val, size=(N_ROWS, N_ROWS), problem="min", cardinality_check=False, _handle=h)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        r = sslap_b200.auction_solve(loc=h_loc, val=h_val, size=(N_ROWS, N_ROWS), problem="min", cardinality_check=False, _handle=h)
-    barrier()
-    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
-    t_e2e = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t_e2e.item())
-    assert np.array_equal(r["sol"], sol)
+
+    def time_api(a_loc, a_val):
+        for _ in range(2):
+            sslap_b200.auction_solve(loc=a_loc, val=a_val, size=(N_ROWS, N_ROWS), problem="min", cardinality_check=False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r = sslap_b200.auction_solve(loc=a_loc, val=a_val, size=(N_ROWS, N_ROWS), problem="min", cardinality_check=False)
+        barrier()
+        assert np.array_equal(r["sol"], sol)
+        return max_over_ranks(1e3 * (time.perf_counter() - t0) / args.steps)
+
+    e2e_ms = time_api(h_loc, h_val)                                        # pinned host memory
+    e2e_pageable_ms = time_api(loc, val)                                   # the literal drop-in call: plain numpy arrays
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    gpu_launches = launches_per_step * args.steps
 
     # ---------------- roofline of the dominant-bandwidth kernel: the full-frontier bidding sweep ----------------
     avg = C.c_float(0)
     rc = L.sslapb_bid_sweep(h.ptr, None, None, N_ROWS, float(np.float32(1.0 / N_ROWS)), 1, 20, 1, None, None, C.byref(avg))
     assert rc == 0
-    sweep_bytes = 12 * nnz + 44 * N_ROWS                                   # 12 B per CSR entry + 44 B per bidder
+    sweep_bytes = 12 * nnz + 36 * N_ROWS               # SURVEY.md §8(d) / DESIGN.md §4.2: 12 B per CSR entry + 36 B per bidder
     peak, peak_src = measured_peaks()
     achieved = sweep_bytes / (avg.value * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic_bytes()
 
-    nnz_total = torch.tensor([float(nnz)], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(nnz_total, op=dist.ReduceOp.SUM)
-    total_nnz = float(nnz_total.item())
+    # ---------------- configs[4]: 4096 independent 512 x 512 problems, dealt out to the ranks ----------------
+    c5 = None
+    if not args.no_c5:
+        from sslap_b200.batch import auction_solve_batch, pack_problems
+        lo, hi = parallel.shard_range(C5_PROBLEMS, world, rank)
+        packed = pack_problems([make_problem(C5_N, C5_DENSITY, "float", seed=k) + ((C5_N, C5_N),) for k in range(lo, hi)])
+        raw = None
+        for _ in range(2):
+            raw = auction_solve_batch(packed, problem="min", packed_result=True)
+        barrier()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            raw = auction_solve_batch(packed, problem="min", packed_result=True)
+        barrier()
+        c5_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / reps)
+        dev_ms = max_over_ranks(float(raw["metas"][0].solve_ms))
+        ok = all(int(m.soln_found) == 1 for m in raw["metas"])
+        c5 = {"workload": f"C5: {C5_PROBLEMS} independent {C5_N} x {C5_N} problems at 5 % (seeds 0..{C5_PROBLEMS - 1}), float costs, min",
+              "problems": C5_PROBLEMS, "problems_per_rank": hi - lo, "parallelism": f"batch shards x{world} (no data-path collective)",
+              "ms_per_batch_e2e": c5_ms, "problems_per_s": C5_PROBLEMS / (c5_ms * 1e-3), "batch_kernel_ms": dev_ms,
+              "h2d_bytes_per_rank": int(packed["loc"].nbytes + packed["val"].nbytes), "all_solved": bool(ok)}
+        gpu_launches += 0                                                   # (outside the timed region of the headline)
+
+    # ---------------- configs[3]: N = 1M, HK check on, row-sharded over all ranks (8 GPUs by default) ----------------
+    c4 = None
+    if args.c4 == "on" or (args.c4 == "auto" and world == 8):
+        try:
+            n4 = 1000000
+            loc4, val4 = make_problem(n4, 1e-4, "float", seed=0)
+            barrier()
+            t0 = time.perf_counter()
+            r4 = sslap_b200.auction_solve(loc=loc4, val=val4, size=(n4, n4), problem="min", cardinality_check=True,
+                                          max_iter=50000000, _raw_meta=True)
+            barrier()
+            c4_s = max_over_ranks(time.perf_counter() - t0)
+            m4 = r4["raw"]
+            c4 = {"workload": "C4: random 1M x 1M, 0.01% density (~101M nnz), float costs, min, Hopcroft-Karp check on",
+                  "nnz": int(val4.size), "wall_s": c4_s, "edges_per_s": int(val4.size) / c4_s, "solve_ms": float(m4.solve_ms),
+                  "hk_ms": float(m4.hk_ms), "h2d_ms": float(m4.h2d_ms), "its": int(m4.its), "cardinality": int(m4.cardinality),
+                  "objective": objective(loc4, val4, r4["sol"]), "rounds_sharded": int(m4.rounds_sharded),
+                  "xchg_ms": float(m4.xchg_ms), "reference": "its 1935709, objective 1630435.704360, 1448 s on one core (BASELINE.md)"}
+            del loc4, val4
+        except Exception as e:                                              # the headline line must survive
+            c4 = {"error": repr(e)[:300]}
 
     if rank == 0:
+        value = nnz / (ms_step * 1e-3)                                      # ONE problem: the job's throughput, not a per-GPU sum
         line = {
-            "metric": "auction_solve_edges_per_s", "value": total_nnz / (ms_step * 1e-3), "unit": "edges/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n": N_ROWS, "nnz_rank0": nnz, "seed": 0, "parallelism": f"replicas x{world}",
-                       "l2": "inputs (162 MB COO + 121 MB CSR per step) exceed the 126 MB L2; sweep leg flushes L2 explicitly",
-                       "its": its, "objective": obj},
+            "metric": "auction_solve_edges_per_s", "value": value, "unit": "edges/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": make_config(nnz, world),
+            "result": {"its": its, "objective": obj},
             "solve_s": ms_step * 1e-3,
             "device_ms": {"csr_build": float(np.mean(setup_ms)), "auction_kernel": float(np.mean(solve_ms)),
                           "rounds": {"grid": int(meta.rounds_grid), "warp": int(meta.rounds_warp), "chain": int(meta.rounds_solo)},
                           "sections_ms": [round(float(x), 3) for x in meta.prof_ms]},
-            "e2e": {"value": total_nnz / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(loc.nbytes + val.nbytes), "d2h_bytes_per_step": int(sol.nbytes + 8 * N_ROWS + 256)},
-            "gpu_launches": 4 * args.steps,          # per step: coo_ingest, rowmax, auction_init, persistent auction kernel
+            "e2e": {"value": nnz / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(loc.nbytes + val.nbytes) * world,
+                    "d2h_bytes_per_step": int(sol.nbytes + 8 * N_ROWS + 512) * world, "host_memory": "pinned"},
+            "e2e_pageable": {"value": nnz / (e2e_pageable_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_pageable_ms,
+                             "host_memory": "pageable numpy arrays, default handle: the literal drop-in call"},
+            "gpu_launches": gpu_launches,
             "roofline": {"kernel": "sslapb_bid_sweep_kernel (full frontier, N bidders, merge atomics on)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic_bytes(), "traffic_source": "profiles/r1_bid_sweep_full_raw_final.csv "
-                         "(ncu --set full of this launch: dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "traffic": traffic, "traffic_source": f"{traffic_src} (ncu --set full of this launch: "
+                         "dram__bytes_read.sum + dram__bytes_write.sum)" if traffic_src else None,
                          "bytes_per_launch": sweep_bytes, "avg_launch_us": avg.value * 1e3,
+                         "insitu": {"what": "bidding step of the full-frontier rounds inside the persistent kernel (512-thread CTAs, "
+                                            "globaltimer, incl. the grid barrier that ends the step); at N>1 each rank sweeps 1/N of the rows",
+                                    "avg_us": float(np.mean(insitu_us)), "rounds_per_solve": int(meta.sweep_insitu_n),
+                                    "achieved": (sweep_bytes / world) / (float(np.mean(insitu_us)) * 1e-6) / 1e9 if np.mean(insitu_us) > 0 else None},
                          "note": "the whole solve is round-latency bound (see device_ms / DESIGN.md); this is the CSR traversal"},
             "clocks": sampler.summary(),
         }
+        if world > 1:
+            line["row_sharding"] = {"rounds_sharded": rounds_sharded, "rank0_rows": row_range, "t_shard": args.t_shard or 16384,
+                                    "exchange_ms_per_solve": float(np.mean(xchg_ms)),
+                                    "sharded_rounds_ms_per_solve": float(np.mean(sharded_ms)),
+                                    "exchange": "in-kernel: peer stores of (object, bid) per list position + system-scope flag barrier"}
+        if c5 is not None:
+            line["c5_batch"] = c5
+        if c4 is not None:
+            line["c4"] = c4
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(loc, val, nnz, sol)
         print(json.dumps(line), flush=True)
     L.sslapb_host_free(p_loc)
     L.sslapb_host_free(p_val)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

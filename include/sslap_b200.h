@@ -17,6 +17,7 @@
  */
 #ifndef SSLAP_B200_H
 #define SSLAP_B200_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -24,6 +25,8 @@ extern "C" {
 #endif
 
 typedef struct sslapb_handle sslapb_handle;
+
+#define SSLAPB_ABI_VERSION 2      /* bumped whenever struct sslapb_meta or a prototype changes */
 
 enum {
     SSLAPB_OK = 0,
@@ -67,14 +70,33 @@ typedef struct sslapb_meta {
     int64_t prune_second_pass; /* grid-regime rows whose bound-pruned sweep needed the second (exactness) gather pass */
     int32_t stop_reason;     /* 1 target-eps CS holds (:275) | 2 eps < target (:280) | 3 max_iter (:309) */
     int32_t rounds_cluster;  /* rounds run by cluster 0 alone (mid-sized frontiers); the others are in rounds_grid/warp/solo */
+    /* ---- ABI version 2 ---- */
+    int32_t n_ranks, rank;   /* row-sharded solve (sslapb_comm_init): size of the communicator and this handle's rank; 1, 0 otherwise */
+    int32_t row_lo, row_hi;  /* ... the nnz-balanced row range [row_lo, row_hi) this rank bids for in sharded rounds */
+    int64_t rounds_sharded;  /* ... rounds (of rounds_grid) whose bidding step was split over the ranks */
+    float   xchg_ms;         /* ... device time CTA 0 spent in the cross-GPU exchange barrier of those rounds (signal + wait) */
+    float   sharded_ms;      /* ... device time of those rounds in total */
+    float   sweep_insitu_us; /* mean device time of the bidding step of the full-frontier rounds (every person bids: first round
+                                of each eps-phase) inside the persistent kernel, incl. the barrier that ends it */
+    int32_t sweep_insitu_n;  /* number of such rounds */
+    int32_t warm_start;      /* 1 when the solve started from caller-supplied prices (sslapb_set_prices) */
+    int32_t strict;          /* 1 when the strict-optimality stop rule was on (option "strict") */
 } sslapb_meta;
 
 int  sslapb_create(int device, sslapb_handle **out);
 void sslapb_destroy(sslapb_handle *h);
 const char *sslapb_last_error(const sslapb_handle *h);
+/* Layout guards for foreign-language bindings: sizeof(struct sslapb_meta) of THIS build and SSLAPB_ABI_VERSION.  A stub must
+   assert both before its first call (a shorter struct on the caller's side would be overrun by the library). */
+size_t sslapb_meta_size(void);
+int    sslapb_abi_version(void);
 /* tuning knobs: "t_small" (frontier size at or below which CTA 0 runs rounds alone, 0..32), "t_cluster" (frontier size
    at or below which one thread-block cluster of 8 CTAs runs the rounds with hardware cluster barriers; 0 = off, the
-   default — opt-in, honoured only while t_small is 32), "watchdog_ms" (device watchdog of a single barrier wait, default 120000) */
+   default — opt-in, honoured only while t_small is 32), "watchdog_ms" (device watchdog of a single barrier wait, default 120000),
+   "t_shard" (row-sharded solves: rounds with more bidders than this are split over the ranks; default 16384),
+   "max_ctas" (upper bound of the persistent kernel's grid, 0 = one CTA per SM; used to co-schedule several solves on one GPU),
+   "strict" (1: strict-optimality stop rule — eps-CS is tested with eps = 1/(N+1) and zero tolerance and the eps schedule runs
+   until eps < 1/(N+1), which makes the result provably optimal for integer costs; 0 = the reference's rule, default) */
 int  sslapb_set_option(sslapb_handle *h, const char *name, int64_t value);
 
 /* Pinned host memory for callers that want asynchronous staging (bench.py's e2e leg). */
@@ -127,6 +149,36 @@ int sslapb_auction_batch(sslapb_handle *h, int32_t n_problems, const int64_t *nn
 
 /* Prices of the most recent solve on this handle (AuctionSolver.p, auction_.pyx:169,220) — n_cols doubles, host. */
 int sslapb_get_prices(sslapb_handle *h, double *prices_out);
+
+/*
+ * Warm start: the NEXT sslapb_auction_coo / _dense call on this handle starts from these object
+ * prices instead of AuctionSolver.__init__'s zeros (auction_.pyx:220); consumed by that one call.  n_cols must equal the
+ * problem's column count (else SSLAPB_E_BAD_ARG at the solve); prices are in the solver's internal (maximisation) frame,
+ * i.e. exactly what sslapb_get_prices returned for a related problem.  prices == NULL clears a pending warm start.
+ * Combine with eps_start (e.g. the final eps of the previous solve) to skip the coarse eps-phases.
+ */
+int sslapb_set_prices(sslapb_handle *h, const double *prices, int32_t n_cols);
+
+/*
+ * Row-sharded solve of ONE problem over several GPUs of a node (the reference has no counterpart: it
+ * replaces the serial merge loop auction_.pyx:367-385 across devices).  SPMD contract: n_ranks handles (one per GPU, in
+ * one or several processes) call sslapb_comm_init, exchange the export blobs by any host-side means (torch.distributed,
+ * MPI, a pipe), call sslapb_comm_connect with all n_ranks blobs in rank order, and from then on make the SAME sequence
+ * of sslapb_auction_coo / _dense calls with the SAME full problem.  Every rank builds the whole CSR and keeps the whole
+ * state; persons are split into nnz-balanced contiguous row ranges (computed on the device from the CSR offsets), and in
+ * rounds whose frontier exceeds option "t_shard" each rank sweeps only its own bidders and stores their bids straight
+ * into every rank's exchange buffer over NVLink (peer-mapped memory: cudaIpc handles across processes, plain peer access
+ * inside one); one in-kernel exchange barrier (system-scope flags) later every rank merges all bids with the same 64-bit
+ * atomicMax and applies the identical assignment, so prices, sol and its stay bit-identical to the single-GPU solve on
+ * every rank.  Smaller frontiers (the latency-bound tail) run redundantly on every rank with no communication.
+ *   capacity_rows: largest n_rows the communicator will see (sizes the exchange buffers: 24 bytes per row per rank).
+ *   export_out:    SSLAPB_COMM_EXPORT_BYTES bytes, opaque.
+ */
+#define SSLAPB_COMM_EXPORT_BYTES 128
+#define SSLAPB_COMM_MAX_RANKS 8
+int sslapb_comm_init(sslapb_handle *h, int n_ranks, int rank, int64_t capacity_rows, void *export_out);
+int sslapb_comm_connect(sslapb_handle *h, const void *all_exports);
+int sslapb_comm_destroy(sslapb_handle *h);
 
 /*
  * Kernel-level entry used by the parity tests and the roofline measurement: one bidding sweep

@@ -38,6 +38,8 @@ def lib():
         L.sslap_oracle_auction.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int,
                                            C.c_float, C.c_int64, C.c_int, C.c_void_p, C.POINTER(OracleMeta),
                                            C.c_void_p, C.c_void_p]
+        L.sslap_oracle_set_ext.restype = None
+        L.sslap_oracle_set_ext.argtypes = [C.c_void_p, C.c_int]
         L.sslap_oracle_hopcroft.restype = C.c_int32
         L.sslap_oracle_hopcroft.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.sslap_oracle_bid_sweep.restype = None
@@ -52,7 +54,7 @@ def _ptr(a):
 
 
 def auction_solve(loc=None, val=None, mat=None, problem="min", eps_start=0.0, max_iter=1000000, fast=False,
-                  faithful_scan=False, return_prices=False, frontier_hist=False):
+                  faithful_scan=False, return_prices=False, frontier_hist=False, prices_in=None, strict=False):
     """CPU oracle of auction_solve (no cardinality check — that is `hopcroft_solve`).  Returns {'sol','meta'} with the
     reference's meta keys and rounding (auction_.pyx:264,297-304) plus unrounded extras under meta['_raw']."""
     if mat is not None:                                   # _from_matrix, auction_.pyx:546-553
@@ -72,6 +74,10 @@ def auction_solve(loc=None, val=None, mat=None, problem="min", eps_start=0.0, ma
     prices = np.empty(M, dtype=np.float64) if return_prices else None
     hist = np.zeros(40, dtype=np.int64) if frontier_hist else None
     meta = OracleMeta()
+    if prices_in is not None or strict:                   # extensions beyond the reference: warm start / strict stop rule
+        prices_in = None if prices_in is None else np.ascontiguousarray(prices_in, dtype=np.float64)
+        assert prices_in is None or prices_in.size == M
+        lib().sslap_oracle_set_ext(_ptr(prices_in) if prices_in is not None else None, int(bool(strict)))
     t0 = time.perf_counter()
     rc = lib().sslap_oracle_auction(_ptr(rows), _ptr(cols), _ptr(val), val.size, N, M, int(problem != "min"),
                                     float(np.float32(eps_start)), int(max_iter), int(bool(faithful_scan)), _ptr(sol),

@@ -13,9 +13,14 @@ LIB_PATH = os.environ.get("SSLAP_B200_LIB", os.path.join(_HERE, "csrc", "libssla
 OK, E_FEWER_THAN_N, E_CARDINALITY, E_UNSORTED, E_BAD_ARG, E_OUT_OF_RANGE, E_EMPTY_ROW, E_ABORTED = range(8)
 MEM_HOST, MEM_DEVICE_IN, MEM_DEVICE_OUT = 0, 1, 2
 
-EXPORTS = ("sslapb_create", "sslapb_destroy", "sslapb_last_error", "sslapb_set_option", "sslapb_host_alloc",
-           "sslapb_host_free", "sslapb_auction_coo", "sslapb_auction_dense", "sslapb_hopcroft_coo",
-           "sslapb_hopcroft_dense", "sslapb_get_prices", "sslapb_bid_sweep", "sslapb_auction_batch")
+ABI_VERSION = 2
+COMM_EXPORT_BYTES, COMM_MAX_RANKS = 128, 8
+
+# every symbol include/sslap_b200.h declares (tests/test_abi.py checks this list against the header)
+EXPORTS = ("sslapb_create", "sslapb_destroy", "sslapb_last_error", "sslapb_meta_size", "sslapb_abi_version",
+           "sslapb_set_option", "sslapb_host_alloc", "sslapb_host_free", "sslapb_auction_coo", "sslapb_auction_dense",
+           "sslapb_hopcroft_coo", "sslapb_hopcroft_dense", "sslapb_auction_batch", "sslapb_get_prices",
+           "sslapb_set_prices", "sslapb_comm_init", "sslapb_comm_connect", "sslapb_comm_destroy", "sslapb_bid_sweep")
 
 
 class Meta(C.Structure):
@@ -27,7 +32,11 @@ class Meta(C.Structure):
                 ("cardinality", C.c_int32), ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("nnz", C.c_int64),
                 ("rounds_grid", C.c_int64), ("rounds_warp", C.c_int64), ("rounds_solo", C.c_int64),
                 ("prof_ms", C.c_float * 8), ("prune_second_pass", C.c_int64),
-                ("stop_reason", C.c_int32), ("rounds_cluster", C.c_int32)]
+                ("stop_reason", C.c_int32), ("rounds_cluster", C.c_int32),
+                ("n_ranks", C.c_int32), ("rank", C.c_int32), ("row_lo", C.c_int32), ("row_hi", C.c_int32),
+                ("rounds_sharded", C.c_int64), ("xchg_ms", C.c_float), ("sharded_ms", C.c_float),
+                ("sweep_insitu_us", C.c_float), ("sweep_insitu_n", C.c_int32), ("warm_start", C.c_int32),
+                ("strict", C.c_int32)]
 
 
 _lib = None
@@ -72,6 +81,22 @@ def load():
     L.sslapb_get_prices.argtypes = [vp, vp]
     L.sslapb_bid_sweep.restype = C.c_int
     L.sslapb_bid_sweep.argtypes = [vp, vp, vp, i32, f32, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(f32)]
+    L.sslapb_meta_size.restype = C.c_size_t
+    L.sslapb_meta_size.argtypes = []
+    L.sslapb_abi_version.restype = C.c_int
+    L.sslapb_abi_version.argtypes = []
+    L.sslapb_set_prices.restype = C.c_int
+    L.sslapb_set_prices.argtypes = [vp, vp, i32]
+    L.sslapb_comm_init.restype = C.c_int
+    L.sslapb_comm_init.argtypes = [vp, C.c_int, C.c_int, i64, vp]
+    L.sslapb_comm_connect.restype = C.c_int
+    L.sslapb_comm_connect.argtypes = [vp, vp]
+    L.sslapb_comm_destroy.restype = C.c_int
+    L.sslapb_comm_destroy.argtypes = [vp]
+    # layout guard: a binding written against another header would be overrun by the library's memset of the meta block
+    if L.sslapb_abi_version() != ABI_VERSION or L.sslapb_meta_size() != C.sizeof(Meta):
+        raise ImportError(f"{LIB_PATH}: ABI {L.sslapb_abi_version()} / sizeof(sslapb_meta) {L.sslapb_meta_size()} does not "
+                          f"match this binding (ABI {ABI_VERSION}, {C.sizeof(Meta)} bytes): rebuild the library")
     _lib = L
     return L
 
@@ -100,6 +125,43 @@ class Handle:
         if rc != 0:
             raise ValueError(f"sslapb_set_option({name}, {value}) -> {rc}: {self.last_error()}")
 
+    def set_prices(self, prices):
+        """Warm start: the next auction call on this handle starts from `prices` (float64, one per column; None clears)."""
+        import numpy as np
+        if prices is None:
+            rc = load().sslapb_set_prices(self._h, None, 0)
+        else:
+            prices = np.ascontiguousarray(prices, dtype=np.float64)
+            rc = load().sslapb_set_prices(self._h, prices.ctypes.data, int(prices.shape[0]))
+        if rc != 0:
+            raise RuntimeError(f"sslapb_set_prices -> {rc}: {self.last_error()}")
+
+    def get_prices(self, n_cols: int):
+        import numpy as np
+        p = np.empty(int(n_cols), dtype=np.float64)
+        rc = load().sslapb_get_prices(self._h, p.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"sslapb_get_prices -> {rc}: {self.last_error()}")
+        return p
+
+    def comm_init(self, n_ranks: int, rank: int, capacity_rows: int) -> bytes:
+        """Create this rank's exchange buffer; returns the opaque export blob to hand to every rank's comm_connect."""
+        buf = C.create_string_buffer(COMM_EXPORT_BYTES)
+        rc = load().sslapb_comm_init(self._h, int(n_ranks), int(rank), int(capacity_rows), buf)
+        if rc != 0:
+            raise RuntimeError(f"sslapb_comm_init -> {rc}: {self.last_error()}")
+        return buf.raw
+
+    def comm_connect(self, exports):
+        """`exports`: the blobs of ALL ranks in rank order."""
+        blob = b"".join(exports)
+        rc = load().sslapb_comm_connect(self._h, blob)
+        if rc != 0:
+            raise RuntimeError(f"sslapb_comm_connect -> {rc}: {self.last_error()}")
+
+    def comm_destroy(self):
+        load().sslapb_comm_destroy(self._h)
+
     def close(self):
         if self._h:
             load().sslapb_destroy(self._h)
@@ -113,7 +175,9 @@ class Handle:
 
 
 def default_handle(device: int = None) -> Handle:
-    """Process-wide handle per device (LOCAL_RANK picks the device under torchrun)."""
+    """Process-wide handle per device (LOCAL_RANK picks the device under torchrun).  Shared by all Python threads: the
+    library serialises concurrent calls on one handle with a per-handle mutex (ctypes releases the GIL), so threads are
+    safe but take turns; give each thread its own `Handle` to overlap their solves."""
     if device is None:
         device = int(os.environ.get("SSLAP_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
     with _lock:

@@ -69,7 +69,8 @@ def _raise_infeasible(rc: int, m: nat.Meta, n_rows_msg: int, h: nat.Handle):
 def auction_solve(mat: np.ndarray = None, loc: np.ndarray = None, val: np.ndarray = None, coo_mat=None,
                   problem: str = 'min', eps_start: float = 0.,
                   max_iter: int = 1000000, fast: bool = False, size=None, cardinality_check=True,
-                  _handle: nat.Handle = None, _raw_meta: bool = False) -> dict:
+                  _handle: nat.Handle = None, _raw_meta: bool = False, prices_in: np.ndarray = None,
+                  return_prices: bool = False) -> dict:
     """Solve an assignment problem i -> j with the eps-scaling auction algorithm on the GPU.
 
     Inputs, keywords, return value and errors are those of the reference's ``sslap.auction_solve``:
@@ -78,8 +79,26 @@ def auction_solve(mat: np.ndarray = None, loc: np.ndarray = None, val: np.ndarra
     ``max_iter``, ``fast``, ``size`` and ``cardinality_check`` as in auction_solve.py:26-35.
     Returns ``{'sol': int32[N], 'meta': {...}}`` (-1 in ``sol`` only if ``max_iter`` was hit).
     Unlike the reference, the caller's ``val`` is never negated in place.
+
+    Extensions (keyword only, not in the reference): ``prices_in`` — warm start from these object prices (as returned by
+    an earlier call with ``return_prices=True``) instead of zeros (auction_.pyx:220), usually together with ``eps_start``;
+    ``return_prices`` — add ``'prices'`` (float64, one per column, AuctionSolver.p) to the result.
     """
     h = _handle or nat.default_handle()
+    if prices_in is None:
+        return _dispatch(h, mat, loc, val, coo_mat, problem, eps_start, max_iter, fast, size, cardinality_check,
+                         _raw_meta, return_prices)
+    h.set_prices(prices_in)
+    try:
+        return _dispatch(h, mat, loc, val, coo_mat, problem, eps_start, max_iter, fast, size, cardinality_check,
+                         _raw_meta, return_prices)
+    finally:
+        h.set_prices(None)                                # consumed by a successful solve; cleared after a failed one
+
+
+def _dispatch(h, mat, loc, val, coo_mat, problem, eps_start, max_iter, fast, size, cardinality_check, _raw_meta,
+              return_prices):
+    """Format dispatch of auction_solve.py:41-55."""
     L = nat.load()
     maximize = int(problem != 'min')
     m = nat.Meta()
@@ -99,11 +118,12 @@ def auction_solve(mat: np.ndarray = None, loc: np.ndarray = None, val: np.ndarra
                                     C.byref(m))
         n_msg = n
     elif loc is not None and val is not None:
-        return _solve_sparse(h, L, loc, val, size, maximize, eps_start, max_iter, fast, cardinality_check, _raw_meta)
+        return _solve_sparse(h, L, loc, val, size, maximize, eps_start, max_iter, fast, cardinality_check, _raw_meta,
+                             return_prices)
     elif coo_mat is not None:                             # auction_solve.py:47-50
         loc = np.stack([coo_mat.row, coo_mat.col], axis=-1)
         return _solve_sparse(h, L, loc, coo_mat.data, coo_mat.shape, maximize, eps_start, max_iter, fast,
-                             cardinality_check, _raw_meta)
+                             cardinality_check, _raw_meta, return_prices)
     else:
         raise ValueError(_FORMAT_ERROR)
     if rc != 0:
@@ -111,10 +131,13 @@ def auction_solve(mat: np.ndarray = None, loc: np.ndarray = None, val: np.ndarra
     out = dict(sol=sol, meta=_meta_dict(m))
     if _raw_meta:
         out["raw"] = m
+    if return_prices:
+        out["prices"] = h.get_prices(m.n_cols)
     return out
 
 
-def _solve_sparse(h, L, loc, val, size, maximize, eps_start, max_iter, fast, cardinality_check, raw_meta):
+def _solve_sparse(h, L, loc, val, size, maximize, eps_start, max_iter, fast, cardinality_check, raw_meta,
+                  return_prices=False):
     """_from_sparse, auction_.pyx:575-617."""
     loc = _as_index_array(loc)
     val = _as_values(val)
@@ -142,4 +165,6 @@ def _solve_sparse(h, L, loc, val, size, maximize, eps_start, max_iter, fast, car
     out = dict(sol=sol, meta=_meta_dict(m))
     if raw_meta:
         out["raw"] = m
+    if return_prices:
+        out["prices"] = h.get_prices(m.n_cols)
     return out

@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 #include <chrono>
+#include <mutex>
+#include <unistd.h>
 
 // ---- kernels' launchers (csr_build.cu / auction.cu / hopcroft.cu)
 
@@ -24,7 +26,8 @@ cudaError_t sslapb_launch_index_max(const void *, const void *, int, long long, 
 cudaError_t sslapb_launch_dense_count(const double *, int, int, long long *, SslapbBuildFlags *, int, cudaStream_t);
 cudaError_t sslapb_launch_dense_fill(const double *, int, int, int, const long long *, int *, double *,
                                      SslapbBuildFlags *, int, cudaStream_t);
-cudaError_t sslapb_launch_auction(const SslapbAuctionParams *, int, int, int, cudaStream_t);
+cudaError_t sslapb_launch_auction(const SslapbAuctionParams *, int, int, int, int, cudaStream_t);
+cudaError_t sslapb_launch_row_split(const long long *, int, int, int *, cudaStream_t);
 int sslapb_coop_row_entries();
 cudaError_t sslapb_auction_grid_size(int, int *);
 cudaError_t sslapb_auction_cluster_grid(int, int *, int *);
@@ -84,6 +87,8 @@ struct DevBuf {
 }  // namespace
 
 struct sslapb_handle {
+    std::recursive_mutex mu;       // every entry point holds it: concurrent calls on ONE handle are serialised (the reference is
+                                   // re-entrant under the GIL; ctypes releases the GIL, so the library must lock)
     int device = 0;
     int sms = 0;
     int grid = 0;
@@ -96,6 +101,20 @@ struct sslapb_handle {
     int cluster = 1;               // CTAs per cluster the device supports for the persistent kernel (1: none)
     int cluster_grid = 0;          // grid of the cluster launch (a multiple of `cluster`)
     long long watchdog_ms = 120000;
+    int t_shard = 16384;           // row-sharded solves: rounds with more bidders than this are split over the ranks
+    int max_ctas = 0;              // upper bound of the persistent kernel's grid (0: one CTA per SM)
+    int strict = 0;                // strict-optimality stop rule (see the header)
+    // warm start: prices for the next solve (sslapb_set_prices)
+    DevBuf warm;
+    int warm_cols = 0;
+    // row-sharded communicator (sslapb_comm_init / _connect)
+    int n_ranks = 1, rank = 0;
+    bool comm_connected = false, comm_broken = false;
+    long long xcap = 0;
+    DevBuf xbuf, xtab, rowsplit;   // exchange buffer (flags | bidv[2][xcap] | bidj[2][xcap]), peer address table, row boundaries
+    void *peer_base[8] = {};       // peer-mapped base address of every rank's exchange buffer
+    bool peer_ipc[8] = {};         // opened with cudaIpcOpenMemHandle (to be closed)
+    unsigned xround = 0;           // sharded rounds completed on this communicator
     // resident problem
     int N = 0, M = 0;
     int maxdeg = 0;                // longest row (read back after the row-maximum pass)
@@ -118,6 +137,8 @@ struct sslapb_handle {
             return -(int)e_;                                                                             \
         }                                                                                                \
     } while (0)
+
+#define LOCK(h) std::lock_guard<std::recursive_mutex> lock_((h)->mu)
 
 static int fail(sslapb_handle *h, int code, const std::string &msg)
 {
@@ -158,6 +179,8 @@ extern "C" void sslapb_destroy(sslapb_handle *h)
                      &h->hole_count, &h->chosen, &h->ctrl, &h->bidders, &h->flush, &h->sweep_plan, &h->pair_u, &h->pair_v, &h->dist,
                      &h->visited, &h->cursor, &h->pred, &h->hkflags};
     for (DevBuf *b : all) b->release();
+    for (int r = 0; r < 8; ++r) if (h->peer_ipc[r] && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+    h->xbuf.release(); h->xtab.release(); h->rowsplit.release(); h->warm.release();
     for (auto &ev : h->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -165,12 +188,20 @@ extern "C" void sslapb_destroy(sslapb_handle *h)
 
 extern "C" const char *sslapb_last_error(const sslapb_handle *h) { return h ? h->err.c_str() : "null handle"; }
 
+// Layout guard for foreign-language bindings: a stub whose struct differs from this size was written against another header.
+extern "C" size_t sslapb_meta_size(void) { return sizeof(sslapb_meta); }
+extern "C" int sslapb_abi_version(void) { return SSLAPB_ABI_VERSION; }
+
 extern "C" int sslapb_set_option(sslapb_handle *h, const char *name, int64_t value)
 {
     if (!h || !name) return SSLAPB_E_BAD_ARG;
+    LOCK(h);
     if (!strcmp(name, "t_cluster")) { if (value < 0 || value > (1 << 20)) return SSLAPB_E_BAD_ARG; h->t_cluster = (int)value; return 0; }
     if (!strcmp(name, "t_small")) { if (value < 0 || value > 32) return SSLAPB_E_BAD_ARG; h->t_small = (int)value; return 0; }
     if (!strcmp(name, "watchdog_ms")) { if (value <= 0) return SSLAPB_E_BAD_ARG; h->watchdog_ms = value; return 0; }
+    if (!strcmp(name, "t_shard")) { if (value < 0 || value > 0x7fffffff) return SSLAPB_E_BAD_ARG; h->t_shard = (int)value; return 0; }
+    if (!strcmp(name, "max_ctas")) { if (value < 0 || value > 65535) return SSLAPB_E_BAD_ARG; h->max_ctas = (int)value; return 0; }
+    if (!strcmp(name, "strict")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->strict = (int)value; return 0; }
     return fail(h, SSLAPB_E_BAD_ARG, std::string("unknown option ") + name);
 }
 
@@ -393,11 +424,13 @@ static int reserve_auction_state(sslapb_handle *h, SslapbAuctionParams &P)
     // opt-in: launch in clusters, a few SMs stay empty (not combined with the long-row instance).  Only with the default
     // t_small = 32: with t_small < 32 AND grid rounds in front of the cluster rounds of a phase the randomized soak
     // (tools/gpu_soak.py cluster) found rare wrong trajectories — an open issue, DESIGN.md 4.1b — so that combination is off.
-    const bool use_cluster = h->cluster > 1 && h->t_cluster > 0 && h->t_small == 32 &&
+    static const bool cluster_any_t_small = getenv("SSLAPB_CLUSTER_ANY_TSMALL") != nullptr;   // soak runs only (tools/gpu_soak.py)
+    const bool use_cluster = h->cluster > 1 && h->t_cluster > 0 && (h->t_small == 32 || cluster_any_t_small) &&
                              !(h->maxdeg > sslapb_coop_row_entries());
     P.cluster = use_cluster ? h->cluster : 1;
     P.t_cluster = use_cluster ? h->t_cluster : 0;
     P.watchdog_ns = (unsigned long long)h->watchdog_ms * 1000000ull;
+    P.nranks = 1; P.rank = 0; P.t_shard = 0x7fffffff; P.rowsplit = nullptr; P.xtab = nullptr; P.xcap = 0; P.xround_base = 0;
     return SSLAPB_OK;
 }
 
@@ -413,18 +446,47 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
     memcpy(&cmax, &F.maxabs, sizeof cmax);
     const float C = (float)cmax;
     float eps = (float)((double)C / 2.0);
-    const float target = (float)(1.0 / (double)N);
+    // strict mode: eps-CS with eps = 1/(N+1) (N * eps < 1: provably optimal for integer costs) and no tolerance
+    const float target = h->strict ? (float)(1.0 / ((double)N + 1.0)) : (float)(1.0 / (double)N);
     if (eps_start > 0) eps = eps_start;
+    const bool long_rows = h->maxdeg > sslapb_coop_row_entries();
+    // ---- warm start: the caller's prices replace the zeros of AuctionSolver.__init__ (:220)
+    const bool warm = h->warm_cols > 0;
+    if (warm) {
+        if (h->warm_cols != h->M) { h->warm_cols = 0; return fail(h, SSLAPB_E_BAD_ARG, "sslapb_set_prices: n_cols differs from the problem's column count"); }
+        CK(cudaMemcpyAsync(P.price, h->warm.p, (size_t)h->M * 8, cudaMemcpyDeviceToDevice, h->stream));
+        h->warm_cols = 0;
+    }
+    // ---- row-sharded solve
+    const bool sharded = h->n_ranks > 1 && !long_rows;
+    if (h->n_ranks > 1) {
+        if (!h->comm_connected) return fail(h, SSLAPB_E_BAD_ARG, "sslapb_comm_init without sslapb_comm_connect");
+        if (h->comm_broken) return fail(h, SSLAPB_E_ABORTED, "the communicator is out of step after an aborted solve: destroy and re-create it");
+        if ((long long)N > h->xcap) return fail(h, SSLAPB_E_BAD_ARG, "n_rows exceeds the communicator's capacity_rows");
+    }
+    if (sharded) {
+        CK(h->rowsplit.reserve((SSLAPB_MAX_RANKS + 1) * sizeof(int)));
+        CK(sslapb_launch_row_split(P.rowptr, N, h->n_ranks, h->rowsplit.as<int>(), h->stream));
+        P.nranks = h->n_ranks; P.rank = h->rank; P.t_shard = h->t_shard; P.rowsplit = h->rowsplit.as<int>();
+        P.xtab = h->xtab.as<unsigned long long>(); P.xcap = h->xcap; P.xround_base = h->xround;
+        P.cluster = 1; P.t_cluster = 0;
+    }
     SslapbCtrl c;
     memset(&c, 0, sizeof c);
     c.nu = N; c.eps = eps; c.target_eps = target; c.theta = 0.15f; c.max_iter = max_iter; c.ece_final = -1;
+    c.tol = h->strict ? 0.0 : 1e-7;                            // auction_.pyx:16
     c.pmin_key[0] = 0x8000000000000000ull;                     // all prices start at +0.0 (auction_.pyx:220)
     c.pmin_key[1] = ~0ull;
     c.pmax_key = 0x8000000000000000ull;
     CK(cudaMemcpyAsync(P.ctrl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
+    if (warm) CK(sslapb_launch_price_bounds(&P, h->stream));   // pruning bounds of the first phase from the caller's prices
+    int grid = P.cluster > 1 ? h->cluster_grid : h->grid;
+    if (h->max_ctas > 0 && h->max_ctas < grid) { grid = h->max_ctas; if (P.cluster > 1) { P.cluster = 1; P.t_cluster = 0; } }
     CK(cudaEventRecord(h->ev[3], h->stream));
-    CK(sslapb_launch_auction(&P, P.cluster > 1 ? h->cluster_grid : h->grid, P.cluster, h->maxdeg > sslapb_coop_row_entries(), h->stream));
+    CK(sslapb_launch_auction(&P, grid, P.cluster, long_rows, warm, h->stream));
     CK(cudaEventRecord(h->ev[4], h->stream));
+    int rs[SSLAPB_MAX_RANKS + 1] = {};
+    if (sharded) CK(cudaMemcpyAsync(rs, h->rowsplit.p, sizeof rs, cudaMemcpyDeviceToHost, h->stream));
     std::vector<double> chosen((size_t)N);
     std::vector<int32_t> sol_tmp;
     int32_t *sol_host = sol_out;
@@ -437,6 +499,10 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
     CK(cudaMemcpyAsync(chosen.data(), P.chosen, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&c, P.ctrl, sizeof c, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (sharded) {
+        h->xround += (unsigned)c.rounds_sharded;
+        if (c.abort_flag) h->comm_broken = true;               // the ranks may have left the solve at different rounds
+    }
     if (c.abort_flag) {
         std::string msg = c.abort_flag == 2 ? "empty row reached the bidding kernel" : "device watchdog fired";
         if (P.cluster > 1) {                                   // where the CTAs of cluster 0 were (barrier count per CTA)
@@ -468,6 +534,13 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
         for (int k = 0; k < 8; ++k) meta->prof_ms[k] = (float)((double)c.prof[k] * 1e-6);
         meta->stop_reason = c.done;
         meta->prune_second_pass = c.prune_second_pass;
+        meta->n_ranks = sharded ? h->n_ranks : 1; meta->rank = sharded ? h->rank : 0;
+        meta->row_lo = sharded ? rs[h->rank] : 0; meta->row_hi = sharded ? rs[h->rank + 1] : N;
+        meta->rounds_sharded = c.rounds_sharded;
+        meta->xchg_ms = (float)((double)c.xchg_ns * 1e-6); meta->sharded_ms = (float)((double)c.sharded_ns * 1e-6);
+        meta->sweep_insitu_n = (int32_t)c.sweep_ns[1];
+        meta->sweep_insitu_us = c.sweep_ns[1] ? (float)((double)c.sweep_ns[0] * 1e-3 / (double)c.sweep_ns[1]) : 0.f;
+        meta->warm_start = warm ? 1 : 0; meta->strict = h->strict;
         (void)assigned;
     }
     return SSLAPB_OK;
@@ -506,6 +579,7 @@ extern "C" int sslapb_auction_coo(sslapb_handle *h, const void *rows, const void
                                   sslapb_meta *meta)
 {
     if (!h) return SSLAPB_E_BAD_ARG;
+    LOCK(h);
     if (!val) return fail(h, SSLAPB_E_BAD_ARG, "val is NULL");
     CK(cudaSetDevice(h->device));
     SslapbBuildFlags F;
@@ -521,6 +595,7 @@ extern "C" int sslapb_auction_dense(sslapb_handle *h, const double *mat, int32_t
                                     sslapb_meta *meta)
 {
     if (!h) return SSLAPB_E_BAD_ARG;
+    LOCK(h);
     CK(cudaSetDevice(h->device));
     SslapbBuildFlags F;
     memset(&F, 0, sizeof F);
@@ -547,6 +622,7 @@ extern "C" int sslapb_hopcroft_coo(sslapb_handle *h, const void *rows, const voi
                                    int32_t *right_out, int32_t *size_out)
 {
     if (!h) return SSLAPB_E_BAD_ARG;
+    LOCK(h);
     CK(cudaSetDevice(h->device));
     SslapbBuildFlags F;
     memset(&F, 0, sizeof F);
@@ -559,6 +635,7 @@ extern "C" int sslapb_hopcroft_dense(sslapb_handle *h, const double *mat, int32_
                                      int32_t *left_out, int32_t *right_out, int32_t *size_out)
 {
     if (!h) return SSLAPB_E_BAD_ARG;
+    LOCK(h);
     CK(cudaSetDevice(h->device));
     SslapbBuildFlags F;
     memset(&F, 0, sizeof F);
@@ -569,10 +646,121 @@ extern "C" int sslapb_hopcroft_dense(sslapb_handle *h, const double *mat, int32_
 
 extern "C" int sslapb_get_prices(sslapb_handle *h, double *prices_out)
 {
-    if (!h || !prices_out || !h->price.p || h->M <= 0) return SSLAPB_E_BAD_ARG;
+    if (!h || !prices_out) return SSLAPB_E_BAD_ARG;
+    LOCK(h);
+    if (!h->price.p || h->M <= 0) return fail(h, SSLAPB_E_BAD_ARG, "no solve has run on this handle");
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync(prices_out, h->price.p, (size_t)h->M * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return SSLAPB_OK;
+}
+
+extern "C" int sslapb_set_prices(sslapb_handle *h, const double *prices, int32_t n_cols)
+{
+    if (!h) return SSLAPB_E_BAD_ARG;
+    LOCK(h);
+    if (!prices) { h->warm_cols = 0; return SSLAPB_OK; }
+    if (n_cols <= 0) return fail(h, SSLAPB_E_BAD_ARG, "sslapb_set_prices: n_cols <= 0");
+    CK(cudaSetDevice(h->device));
+    CK(h->warm.reserve((size_t)n_cols * 8));
+    CK(cudaMemcpyAsync(h->warm.p, prices, (size_t)n_cols * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->warm_cols = n_cols;
+    return SSLAPB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Row-sharded communicator: one exchange buffer per rank, peer-mapped into every other rank (see the header)
+// ----------------------------------------------------------------------------------------------------------------------
+namespace {
+struct CommExport {                 // SSLAPB_COMM_EXPORT_BYTES
+    unsigned long long magic;
+    long long pid;
+    int device, rank, n_ranks, pad;
+    unsigned long long base;        // device address of the exchange buffer (valid inside the exporting process)
+    long long xcap;
+    cudaIpcMemHandle_t ipc;         // 64 bytes
+    char fill[SSLAPB_COMM_EXPORT_BYTES - 48 - 64];
+};
+static_assert(sizeof(CommExport) == SSLAPB_COMM_EXPORT_BYTES, "export blob size");
+const unsigned long long COMM_MAGIC = 0x53534c4150423230ull;
+size_t xbuf_bytes(long long cap) { return 128 + (size_t)cap * 2 * 8 + (size_t)cap * 2 * 4; }
+}
+
+extern "C" int sslapb_comm_destroy(sslapb_handle *h)
+{
+    if (!h) return SSLAPB_E_BAD_ARG;
+    LOCK(h);
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (int r = 0; r < 8; ++r) {
+        if (h->peer_ipc[r] && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+        h->peer_ipc[r] = false; h->peer_base[r] = nullptr;
+    }
+    h->xbuf.release(); h->xtab.release();
+    h->n_ranks = 1; h->rank = 0; h->comm_connected = false; h->comm_broken = false; h->xcap = 0; h->xround = 0;
+    return SSLAPB_OK;
+}
+
+extern "C" int sslapb_comm_init(sslapb_handle *h, int n_ranks, int rank, int64_t capacity_rows, void *export_out)
+{
+    if (!h) return SSLAPB_E_BAD_ARG;
+    LOCK(h);
+    if (n_ranks < 1 || n_ranks > SSLAPB_COMM_MAX_RANKS || rank < 0 || rank >= n_ranks || capacity_rows <= 0 || !export_out)
+        return fail(h, SSLAPB_E_BAD_ARG, "sslapb_comm_init: bad arguments");
+    sslapb_comm_destroy(h);
+    CK(cudaSetDevice(h->device));
+    CK(h->xbuf.reserve(xbuf_bytes(capacity_rows)));
+    CK(cudaMemsetAsync(h->xbuf.p, 0, xbuf_bytes(capacity_rows), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_ranks = n_ranks; h->rank = rank; h->xcap = capacity_rows;
+    CommExport e;
+    memset(&e, 0, sizeof e);
+    e.magic = COMM_MAGIC; e.pid = (long long)getpid(); e.device = h->device; e.rank = rank; e.n_ranks = n_ranks;
+    e.base = (unsigned long long)h->xbuf.p; e.xcap = capacity_rows;
+    if (n_ranks > 1) CK(cudaIpcGetMemHandle(&e.ipc, h->xbuf.p));
+    memcpy(export_out, &e, sizeof e);
+    return SSLAPB_OK;
+}
+
+extern "C" int sslapb_comm_connect(sslapb_handle *h, const void *all_exports)
+{
+    if (!h || !all_exports) return SSLAPB_E_BAD_ARG;
+    LOCK(h);
+    if (h->xcap <= 0) return fail(h, SSLAPB_E_BAD_ARG, "sslapb_comm_connect before sslapb_comm_init");
+    CK(cudaSetDevice(h->device));
+    const CommExport *E = reinterpret_cast<const CommExport *>(all_exports);
+    unsigned long long tab[3 * SSLAPB_MAX_RANKS] = {};
+    for (int r = 0; r < h->n_ranks; ++r) {
+        const CommExport &e = E[r];
+        if (e.magic != COMM_MAGIC || e.rank != r || e.n_ranks != h->n_ranks || e.xcap != h->xcap)
+            return fail(h, SSLAPB_E_BAD_ARG, "sslapb_comm_connect: export blob " + std::to_string(r) + " does not belong to this communicator");
+        void *base = nullptr;
+        if (r == h->rank) base = h->xbuf.p;
+        else if (e.pid == (long long)getpid()) {               // same process: plain peer access
+            base = (void *)e.base;
+            if (e.device != h->device) {
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can, h->device, e.device));
+                if (!can) return fail(h, SSLAPB_E_BAD_ARG, "no peer access between the devices of ranks " + std::to_string(h->rank) + " and " + std::to_string(r));
+                cudaError_t pe = cudaDeviceEnablePeerAccess(e.device, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CK(pe);
+                cudaGetLastError();
+            }
+        } else {                                               // another process: CUDA IPC mapping (enables peer access lazily)
+            CK(cudaIpcOpenMemHandle(&base, e.ipc, cudaIpcMemLazyEnablePeerAccess));
+            h->peer_ipc[r] = true;
+        }
+        h->peer_base[r] = base;
+        char *b = (char *)base;
+        tab[3 * r] = (unsigned long long)b;                                            // flags
+        tab[3 * r + 2] = (unsigned long long)(b + 128);                                // bidv[2][xcap]
+        tab[3 * r + 1] = (unsigned long long)(b + 128 + (size_t)h->xcap * 2 * 8);      // bidj[2][xcap]
+    }
+    CK(h->xtab.reserve(sizeof tab));
+    CK(cudaMemcpyAsync(h->xtab.p, tab, sizeof tab, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->comm_connected = true; h->comm_broken = false; h->xround = 0;
     return SSLAPB_OK;
 }
 
@@ -580,7 +768,9 @@ extern "C" int sslapb_bid_sweep(sslapb_handle *h, const double *prices, const in
                                 int merge, int iters, int flush_l2, int32_t *jbest_out, double *bid_out,
                                 float *avg_ms_out)
 {
-    if (!h || h->N <= 0 || !h->has_vals || nb <= 0 || iters < 1) return fail(h, SSLAPB_E_BAD_ARG, "no resident problem / bad arguments");
+    if (!h) return SSLAPB_E_BAD_ARG;
+    LOCK(h);
+    if (h->N <= 0 || !h->has_vals || nb <= 0 || iters < 1) return fail(h, SSLAPB_E_BAD_ARG, "no resident problem / bad arguments");
     if (!bidders && nb > h->N) return fail(h, SSLAPB_E_BAD_ARG, "nb > N");
     CK(cudaSetDevice(h->device));
     SslapbAuctionParams P;
@@ -638,6 +828,7 @@ extern "C" int sslapb_auction_batch(sslapb_handle *h, int32_t n_problems, const 
                                     int32_t *sol_out, sslapb_meta *metas)
 {
     if (!h) return SSLAPB_E_BAD_ARG;
+    LOCK(h);
     if (n_problems <= 0 || !nnz_offsets || !n_rows || !n_cols || !rows || !cols || !val || !sol_out)
         return fail(h, SSLAPB_E_BAD_ARG, "bad batch arguments");
     CK(cudaSetDevice(h->device));

@@ -132,10 +132,8 @@ __device__ __forceinline__ int warp_resolve(const SslapbAuctionParams &P, int nu
     long long nst = lst;
     int ndg = ldg;
     if (win) {
-        SslapbObjRec r;
-        r.start = lst; r.owner = li; r.deg = ldg; r.price = bid; r.pad = 0;
-        *reinterpret_cast<int4 *>(P.rec + j) = *reinterpret_cast<const int4 *>(&r);      // owner + its row (:418)
-        P.rec[j].price = bid;                                  // :397
+        sslapb_st_rec256(P.rec + j, (unsigned long long)lst, ((unsigned long long)(unsigned)ldg << 32) | (unsigned)li,
+                         (unsigned long long)__double_as_longlong(bid));   // owner + its row (:418), price (:397)
         P.price[j] = bid;
         P.p2o[li] = j;                                         // :417
         if (B.powner >= 0) P.p2o[B.powner] = -1;               // :404
@@ -249,10 +247,9 @@ __device__ __forceinline__ bool sweep_single(const SslapbAuctionParams &P, const
 // The winner's writes (auction_.pyx:397-418) — executed by one lane.
 __device__ __forceinline__ void commit_win(const SslapbAuctionParams &P, int person, long long st, int dg, const SslapbBid &B)
 {
-    SslapbObjRec r;
-    r.start = st; r.owner = person; r.deg = dg; r.price = B.bid; r.pad = 0;
-    *reinterpret_cast<int4 *>(P.rec + B.j) = *reinterpret_cast<const int4 *>(&r);        // owner + its row (:418)
-    P.rec[B.j].price = B.bid;                                  // :397
+    // the whole 32-byte record in ONE store (a reader's single 256-bit load can never see it torn)
+    sslapb_st_rec256(P.rec + B.j, (unsigned long long)st, ((unsigned long long)(unsigned)dg << 32) | (unsigned)person,
+                     (unsigned long long)__double_as_longlong(B.bid));   // owner + its row (:418), price (:397)
     P.price[B.j] = B.bid;
     P.p2o[person] = B.j;                                       // :417
     if (B.powner >= 0) P.p2o[B.powner] = -1;                   // :404
@@ -462,7 +459,16 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
         const long long nst_b = wonb ? O.pstart : O.st;
         const int ndg_b = wonb ? O.pdeg : O.dg;
         const bool won = __shfl_sync(SSLAPB_FULL, (int)wonb, a) != 0;
-        if (won && lane == 0) commit_win(P, me, st, dg, B);
+        // Commits (:397-418).  EVERY active warp stores EVERY winner's record (lane b commits publication b; all warps
+        // write identical values), so that the loads of a warp's next sweep are ordered after the commits by its own
+        // program order + __syncwarp — no second barrier, and no window in which a loser re-sweeps an object whose
+        // winner (another warp) has not stored the new price yet.
+        if (wonb) {
+            SslapbBid Wb;
+            Wb.j = O.j; Wb.bid = O.bid; Wb.powner = O.powner; Wb.pdeg = O.pdeg; Wb.pstart = O.pstart;
+            commit_win(P, O.me, O.st, O.dg, Wb);
+        }
+        __syncwarp();
         ++its; ++rounds;
         if (its >= max_iter) done = 3;
         // compaction (:429-430): the k-th hole left of the new count takes the k-th live entry right of it
@@ -539,7 +545,14 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
             const bool contested = O.j == B.j;
             const bool won = !contested || B.bid > O.bid || (B.bid == O.bid && a == 0);
             const bool owon = !contested || !won;
-            if (won && lane == 0) commit_win(P, me, st, dg, B);
+            // both warps store BOTH commits (identical values): each warp's next sweep is then ordered after them by
+            // its own program order + __syncwarp (see the 3..16 loop)
+            if ((lane == 0 && won) || (lane == 1 && owon)) {
+                SslapbBid Wb;
+                if (lane == 0) Wb = B; else { Wb.j = O.j; Wb.bid = O.bid; Wb.powner = O.powner; Wb.pdeg = O.pdeg; Wb.pstart = O.pstart; }
+                commit_win(P, lane == 0 ? me : O.me, lane == 0 ? st : O.st, lane == 0 ? dg : O.dg, Wb);
+            }
+            __syncwarp();
             // next occupant of my slot / of the other slot (-1 = hole)
             const int nme = won ? B.powner : me, ome = owon ? O.powner : O.me;
             ++its; ++rounds;
@@ -932,6 +945,66 @@ __device__ __forceinline__ int block_excl_scan_flag(bool flag, int &total)
     return s_wtot[warp] + inwarp;
 }
 
+#ifdef SSLAPB_SHARDED
+// ----------------------------------------------------------------------------------------------------------------------
+// Cross-GPU exchange barrier of a row-sharded round (round number k of this communicator, monotone).  Before it every
+// rank has stored the bids of ITS bidders into every rank's exchange buffer (plain stores to peer-mapped memory over
+// NVLink).  Protocol: local grid barrier arrive (each CTA fences at system scope first, so the release is cumulative over
+// its warps' peer stores) -> CTA 0, once all local CTAs have arrived, publishes k in word `rank` of every peer's flag
+// block (st.release.sys) -> every CTA waits until all of its OWN flag words show k (ld.acquire.sys on local memory).
+// A rank can be at most one sharded round ahead of any other (it needs their flag for round k to leave round k), which is
+// why the exchange buffers have two parity halves.  Returns false when the solve was aborted (watchdog).
+// ----------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool cross_barrier(const SslapbAuctionParams &P, SslapbCtrl *c, unsigned nblk, unsigned &epoch, unsigned k)
+{
+    __shared__ int s_xabort;
+    epoch += nblk;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int ab = 0;
+        const unsigned target = epoch;
+        __threadfence_system();
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(&c->bar_count) : "memory");
+        unsigned polls = 0;
+        unsigned long long t0 = sslapb_globaltimer();
+        while ((int)(sslapb_ld_acquire_u32(&c->bar_count) - target) < 0) {
+            if (++polls < 1024) continue;
+            polls = 0;
+            if (sslapb_ld_volatile_s32(&c->abort_flag)) { ab = 1; break; }
+            if (sslapb_globaltimer() - t0 > P.watchdog_ns) { *(volatile int *)&c->abort_flag = 1; ab = 1; break; }
+        }
+        unsigned long long tx0 = 0;
+        if (blockIdx.x == 0) {
+            tx0 = sslapb_globaltimer();
+            __threadfence_system();
+            for (int r = 0; r < P.nranks; ++r) {
+                if (r == P.rank) continue;
+                unsigned *pf = reinterpret_cast<unsigned *>(__ldg(P.xtab + 3 * r)) + P.rank;
+                asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(pf), "r"(k) : "memory");
+            }
+        }
+        const unsigned *mf = reinterpret_cast<const unsigned *>(__ldg(P.xtab + 3 * P.rank));
+        for (int r = 0; r < P.nranks && !ab; ++r) {
+            if (r == P.rank) continue;
+            polls = 0;
+            for (;;) {
+                unsigned v;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mf + r) : "memory");
+                if ((int)(v - k) >= 0) break;
+                if (++polls < 1024) continue;
+                polls = 0;
+                if (sslapb_ld_volatile_s32(&c->abort_flag)) { ab = 1; break; }
+                if (sslapb_globaltimer() - t0 > P.watchdog_ns) { *(volatile int *)&c->abort_flag = 1; ab = 1; break; }
+            }
+        }
+        if (blockIdx.x == 0) c->xchg_ns += sslapb_globaltimer() - tx0;
+        s_xabort = ab | sslapb_ld_volatile_s32(&c->abort_flag);
+    }
+    __syncthreads();
+    return s_xabort == 0;
+}
+#endif
+
 // One Jacobi round with the bidders spread over several CTAs (auction_.pyx:337-430) — by the whole grid (grid barriers) or,
 // for mid-sized frontiers, by the CTAs of cluster 0 alone (hardware cluster barriers, ~0.25 us instead of ~1.5 us each;
 // the other CTAs wait at one grid barrier for the cluster to hand the phase over).
@@ -952,7 +1025,8 @@ __device__ __forceinline__ bool round_barrier(SslapbCtrl *C, unsigned nblk, unsi
 }
 template <bool CLUSTER>
 __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, SslapbCtrl *C, const SslapbScope S, int nu, float eps_f,
-                                             long long its, long long max_iter, double pmin, double spread, unsigned &bar_epoch)
+                                             long long its, long long max_iter, double pmin, double spread, unsigned &bar_epoch,
+                                             unsigned &xround)
 {
     __shared__ int s_red, s_tie;
     __shared__ int s_hpre[3];
@@ -963,11 +1037,38 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
     unsigned long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0, tp5 = 0;
     if (S.lead) tp0 = sslapb_globaltimer();
     int n2nd = 0;
+    int *bidj = P.bidj;                                // per list position: object / bid of this round
+    double *bidv = P.bidv;
+#ifdef SSLAPB_SHARDED
+    // Row-sharded round (several GPUs, large frontier): this rank sweeps only the bidders of its own row range and stores
+    // each bid into every rank's exchange buffer; after the exchange barrier every rank holds all nu bids and performs the
+    // merge, the assignment and the compaction identically (the whole state is replicated, the trajectory is unchanged).
+    const bool sharded = !CLUSTER && P.nranks > 1 && nu > P.t_shard;
+    int row_lo = 0, row_hi = 0x7fffffff;
+    unsigned xk = 0;
+    long long xoff = 0;
+    if (sharded) {
+        xk = ++xround;
+        xoff = (long long)(xk & 1u) * P.xcap;
+        row_lo = __ldg(P.rowsplit + P.rank); row_hi = __ldg(P.rowsplit + P.rank + 1);
+        bidj = reinterpret_cast<int *>(__ldg(P.xtab + 3 * P.rank + 1)) + xoff;
+        bidv = reinterpret_cast<double *>(__ldg(P.xtab + 3 * P.rank + 2)) + xoff;
+    }
+#endif
     // (1) bidding: warp per list position (auction_.pyx:339-365) + per-object atomicMax merge (:375-385)
     auto emit_bid = [&](int a, int j, double bid) {
+#ifdef SSLAPB_SHARDED
+                        if (sharded) {                 // lane r stores the bid into rank r's buffer (one instruction for all ranks)
+                            if (lane < P.nranks) {
+                                reinterpret_cast<int *>(__ldg(P.xtab + 3 * lane + 1))[xoff + a] = j;
+                                reinterpret_cast<double *>(__ldg(P.xtab + 3 * lane + 2))[xoff + a] = bid;
+                            }
+                            return;
+                        }
+#endif
                         if (lane == 0) {
-                            P.bidj[a] = j;
-                            P.bidv[a] = bid;
+                            bidj[a] = j;
+                            bidv[a] = bid;
                             if (j >= 0) {
                                 const unsigned long long key = sslapb_ord64(bid);
                                 const unsigned long long old = atomicMax(P.bidkey + j, key);
@@ -981,6 +1082,9 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
     for (int a = S.gwarp; a < nu; a += S.nwarps) {
         int v = P.list[a];
         if (v < -1) { v = P.mover[-(v + 2)]; if (lane == 0) P.list[a] = v; }   // hole filled by the last compaction
+#ifdef SSLAPB_SHARDED
+        if (v < row_lo || v >= row_hi) continue;       // another rank's person (every rank still decodes every hole above)
+#endif
         const long long st = __ldg(P.rowptr + v), en = __ldg(P.rowptr + v + 1);
         int j; double bid;
         if ((((en + 3) >> 2) - (st >> 2)) <= 32) {
@@ -996,8 +1100,29 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
     }
     if (n2nd && lane == 0) atomicAdd((unsigned long long *)&C->prune_second_pass, (unsigned long long)n2nd);
     if (S.lead) tp1 = sslapb_globaltimer();
+#ifdef SSLAPB_SHARDED
+    if (sharded) {
+        if (!cross_barrier(P, C, (unsigned)S.nblk, bar_epoch, xk)) return false;
+        // merge (:375-385) over ALL nu bids, identically on every rank
+        for (int a = blockIdx.x * blockDim.x + tid; a < nu; a += S.nblk * blockDim.x) {
+            const int j = bidj[a];
+            if (j >= 0) {
+                const unsigned long long key = sslapb_ord64(bidv[a]);
+                const unsigned long long old = atomicMax(P.bidkey + j, key);
+                if (old == key) *(volatile int *)&C->tie_flag = 1;
+            } else {
+                *(volatile int *)&C->abort_flag = 2;   // empty row: rejected at CSR build
+            }
+        }
+    }
+#endif
     if (!round_barrier<CLUSTER>(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return false;
-    if (S.lead) tp2 = sslapb_globaltimer();
+    if (S.lead) {
+        tp2 = sslapb_globaltimer();
+        // in-situ full-frontier bidding step (every person bids: first round of an eps-phase), up to the barrier that
+        // proves every CTA has finished its rows — no launch ramp, no tail outside the barrier
+        if (nu == P.N) { C->sweep_ns[0] += tp2 - tp0; C->sweep_ns[1] += 1; }
+    }
     if (tid == 0) s_tie = *(volatile int *)&C->tie_flag;
     __syncthreads();
     const int tie = __shfl_sync(SSLAPB_FULL, s_tie, 0);
@@ -1005,25 +1130,24 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
     const int lo = min(nu, S.blk * L), hi = min(nu, lo + L);
     if (tie) {                                         // (1b) equal best bids: earliest list position wins (:379)
         for (int a = lo + tid; a < hi; a += blockDim.x) {
-            const int j = P.bidj[a];
-            if (P.bidkey[j] == sslapb_ord64(P.bidv[a])) atomicMin(P.winpos + j, a);
+            const int j = bidj[a];
+            if (P.bidkey[j] == sslapb_ord64(bidv[a])) atomicMin(P.winpos + j, a);
         }
         if (!round_barrier<CLUSTER>(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return false;
     }
     // (2) assignment (:394-427), by the winner's own list position
     int myholes = 0;
     for (int a = lo + tid; a < hi; a += blockDim.x) {
-        const int j = P.bidj[a];
-        const double bid = P.bidv[a];
+        const int j = bidj[a];
+        const double bid = bidv[a];
         const bool win = (P.bidkey[j] == sslapb_ord64(bid)) && (!tie || P.winpos[j] == a);
         if (win) {
             const int i = P.list[a];
             const int prev = P.rec[j].owner;
-            SslapbObjRec r;
-            r.start = __ldg(P.rowptr + i); r.owner = i; r.deg = (int)(__ldg(P.rowptr + i + 1) - r.start);
-            r.price = bid; r.pad = 0;
-            *reinterpret_cast<int4 *>(P.rec + j) = *reinterpret_cast<const int4 *>(&r);
-            P.rec[j].price = bid;
+            const long long rst = __ldg(P.rowptr + i);
+            const int rdg = (int)(__ldg(P.rowptr + i + 1) - rst);
+            sslapb_st_rec256(P.rec + j, (unsigned long long)rst, ((unsigned long long)(unsigned)rdg << 32) | (unsigned)i,
+                             (unsigned long long)__double_as_longlong(bid));
             P.price[j] = bid;
             P.p2o[i] = j;
             if (prev >= 0) P.p2o[prev] = -1; else ++myholes;
@@ -1094,6 +1218,9 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
         if (CLUSTER) C->rounds_cluster += 1; else C->rounds_grid += 1;
         if (its + 1 >= max_iter) C->done = 3;
         tp5 = sslapb_globaltimer();
+#ifdef SSLAPB_SHARDED
+        if (sharded) { C->rounds_sharded += 1; C->sharded_ns += tp5 - tp0; }
+#endif
     }
     if (!round_barrier<CLUSTER>(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return false;
     if (S.lead && !CLUSTER) {
@@ -1112,6 +1239,9 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
 #ifdef SSLAPB_CLUSTER_REGIME
 #define sslapb_auction_kernel sslapb_auction_kernel_cluster   // third instance, see auction_cluster.cu
 #endif
+#ifdef SSLAPB_SHARDED
+#define sslapb_auction_kernel sslapb_auction_kernel_sharded   // row-sharded multi-GPU instance, see auction_sharded.cu
+#endif
 __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(SslapbAuctionParams P)
 {
     SslapbCtrl *C = P.ctrl;
@@ -1124,6 +1254,7 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
     const int nthreads = nblk * blockDim.x;
     __shared__ struct { int nu, done, nred, tie; float eps; long long its, max_iter; unsigned long long pmin0, pmin1, pmax; } s_top;
     unsigned bar_epoch = 0;                                    // barriers passed so far * #CTAs (wraps harmlessly)
+    unsigned xround = P.xround_base;                           // row-sharded rounds of this communicator so far (all CTAs agree)
 
     if (gtid == 0) C->t_begin = sslapb_globaltimer();
 #ifdef SSLAPB_CLUSTER_REGIME
@@ -1166,7 +1297,7 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
 #endif
             // ================================ grid regime: one round ================================
             const SslapbScope S = {(int)blockIdx.x, (int)nblk, gwarp, nwarps, gtid == 0};
-            if (!spread_round<false>(P, C, S, nu, eps_f, its, max_iter, pmin, spread, bar_epoch)) return;
+            if (!spread_round<false>(P, C, S, nu, eps_f, its, max_iter, pmin, spread, bar_epoch, xround)) return;
 #ifdef SSLAPB_CLUSTER_REGIME
         } else if (nu > P.t_small) {
             // ================================ cluster regime: cluster 0 runs rounds until nu <= t_small ================================
@@ -1177,7 +1308,7 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
                 int cnu = nu, cdone = 0;
                 long long cits = its;
                 while (!cdone && cnu > P.t_small) {
-                    spread_round<true>(P, C, S, cnu, eps_f, cits, max_iter, pmin, spread, bar_epoch);
+                    spread_round<true>(P, C, S, cnu, eps_f, cits, max_iter, pmin, spread, bar_epoch, xround);
                     if (tid == 0) { s_top.nu = *(volatile int *)&C->nu; s_top.done = *(volatile int *)&C->done; s_top.its = *(volatile long long *)&C->its; }
                     __syncthreads();
                     cnu = __shfl_sync(SSLAPB_FULL, s_top.nu, 0);
@@ -1207,14 +1338,14 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
             unsigned long long te0 = 0;
             if (gtid == 0) te0 = sslapb_globaltimer();
             const float teps = *(volatile float *)&C->target_eps;
-            const double eps_t = (double)teps;
+            const double eps_t = (double)teps, tol = *(volatile double *)&C->tol;
             bool viol = false;
             for (int i = gwarp; i < P.N; i += nwarps) {        // eCE_satisfied(target_eps), :443-485
                 const int j = P.p2o[i];
                 const long long st = __ldg(P.rowptr + i), en = __ldg(P.rowptr + i + 1);
                 double vmax, choice, csum;
                 row_ece(P.cols, P.vals, P.price, st, en, lane, j, vmax, choice, csum);
-                const double lhs = (choice - P.price[j]) + 1e-7;
+                const double lhs = (choice - P.price[j]) + tol;
                 if (lhs < vmax - eps_t) viol = true;
             }
             if (viol && lane == 0) *(volatile int *)&C->ece_viol = 1;
@@ -1262,7 +1393,7 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
     {
         const int nu = *(volatile int *)&C->nu;
         const bool need_ece = (*(volatile int *)&C->ece_final < 0) && nu == 0;   // max_iter hit on a full assignment
-        const double eps_t = (double)(*(volatile float *)&C->target_eps);
+        const double eps_t = (double)(*(volatile float *)&C->target_eps), tol = *(volatile double *)&C->tol;
         bool viol = false;
         for (int i = gwarp; i < P.N; i += nwarps) {
             const int j = P.p2o[i];
@@ -1271,7 +1402,7 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
                 const long long st = __ldg(P.rowptr + i), en = __ldg(P.rowptr + i + 1);
                 double vmax, choice;
                 row_ece(P.cols, P.vals, P.price, st, en, lane, j, vmax, choice, csum);
-                if (need_ece && ((choice - P.price[j]) + 1e-7 < vmax - eps_t)) viol = true;
+                if (need_ece && ((choice - P.price[j]) + tol < vmax - eps_t)) viol = true;
             }
             if (lane == 0) P.chosen[i] = csum;
         }
@@ -1304,6 +1435,31 @@ extern "C" cudaError_t sslapb_launch_auction_long(const SslapbAuctionParams *P, 
     return launch_persistent(P, grid, 1, stream);
 }
 extern "C" int sslapb_coop_row_entries() { return 4 * SSLAPB_COOP_CHUNKS - 3; }
+#elif defined(SSLAPB_SHARDED)
+extern "C" cudaError_t sslapb_launch_auction_sharded(const SslapbAuctionParams *P, int grid, cudaStream_t stream)
+{
+    return launch_persistent(P, grid, 1, stream);
+}
+// nnz-balanced contiguous row split (the device-side counterpart of cumulative_idxs' row partition, auction_.pyx:33-48):
+// boundary r = first row whose CSR offset reaches r * nnz / parts (binary search over rowptr, one thread per boundary).
+__global__ void sslapb_row_split_kernel(const long long *__restrict__ rowptr, int N, int parts, int *__restrict__ split)
+{
+    const int r = threadIdx.x;
+    if (r > parts) return;
+    if (r == parts) { split[r] = N; return; }
+    const long long nnz = rowptr[N], target = (nnz / parts) * r + ((nnz % parts) * r) / parts;
+    int lo = 0, hi = N;                                        // first row with rowptr[row] >= target
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (rowptr[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    split[r] = lo;
+}
+extern "C" cudaError_t sslapb_launch_row_split(const long long *rowptr, int N, int parts, int *split, cudaStream_t stream)
+{
+    sslapb_row_split_kernel<<<1, 32, 0, stream>>>(rowptr, N, parts, split);
+    return cudaGetLastError();
+}
 #elif defined(SSLAPB_CLUSTER_REGIME)
 extern "C" cudaError_t sslapb_launch_auction_cluster(const SslapbAuctionParams *P, int grid, int cluster, cudaStream_t stream)
 {
@@ -1392,13 +1548,15 @@ __global__ void __launch_bounds__(1024, 1) sslapb_bid_sweep_kernel(SslapbAuction
 }
 
 // Initial state of a solve (AuctionSolver.__init__, auction_.pyx:220-261).
-__global__ void sslapb_auction_init_kernel(SslapbAuctionParams P)
+// warm != 0: price[] already holds the caller's start prices (sslapb_set_prices) — the reference starts from zeros (:220)
+__global__ void sslapb_auction_init_kernel(SslapbAuctionParams P, int warm)
 {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, n = gridDim.x * blockDim.x;
     for (int i = gtid; i < P.N; i += n) { P.p2o[i] = -1; P.list[i] = i; }
     for (int j = gtid; j < P.M; j += n) {
-        SslapbObjRec r; r.start = 0; r.owner = -1; r.deg = 0; r.price = 0.0; r.pad = 0;
-        P.rec[j] = r; P.price[j] = 0.0; P.bidkey[j] = 0ull; P.winpos[j] = 0x7fffffff;
+        const double p0 = warm ? P.price[j] : 0.0;
+        SslapbObjRec r; r.start = 0; r.owner = -1; r.deg = 0; r.price = p0; r.pad = 0;
+        P.rec[j] = r; P.price[j] = p0; P.bidkey[j] = 0ull; P.winpos[j] = 0x7fffffff;
     }
 }
 
@@ -1406,10 +1564,12 @@ extern "C" cudaError_t sslapb_launch_auction_long(const SslapbAuctionParams *P, 
 extern "C" cudaError_t sslapb_launch_auction_cluster(const SslapbAuctionParams *P, int grid, int cluster, cudaStream_t stream);
 // Three instances of the persistent kernel: this one (lean), auction_long.cu (the longest row exceeds
 // sslapb_coop_row_entries() entries) and auction_cluster.cu (opt-in cluster regime, cluster > 1).
-extern "C" cudaError_t sslapb_launch_auction(const SslapbAuctionParams *P, int grid, int cluster, int long_rows, cudaStream_t stream)
+extern "C" cudaError_t sslapb_launch_auction_sharded(const SslapbAuctionParams *P, int grid, cudaStream_t stream);
+extern "C" cudaError_t sslapb_launch_auction(const SslapbAuctionParams *P, int grid, int cluster, int long_rows, int warm, cudaStream_t stream)
 {
-    sslapb_auction_init_kernel<<<grid, 1024, 0, stream>>>(*P);
+    sslapb_auction_init_kernel<<<grid, 1024, 0, stream>>>(*P, warm);
     if (long_rows) return sslapb_launch_auction_long(P, grid, stream);
+    if (P->nranks > 1) return sslapb_launch_auction_sharded(P, grid, stream);
     if (cluster > 1) return sslapb_launch_auction_cluster(P, grid, cluster, stream);
     return launch_persistent(P, grid, 1, stream);
 }

@@ -33,6 +33,11 @@ struct SslapbCtrl {
                                                        // ((round << 3) | barrier index), reported when the watchdog fires
     unsigned long long prof[8];                        // ns spent (CTA 0 view): 0 grid bid, 1 grid tie+assign, 2 grid compaction,
                                                        // 3 warp regime, 4 solo regime, 5 eCE/phase change, 6 cluster regime, 7 barriers of the grid regime
+    long long rounds_sharded;                          // row-sharded solve: rounds whose bidding was split over the ranks
+    unsigned long long xchg_ns;                        // ... ns CTA 0 spent in their cross-GPU exchange barrier (signal + wait)
+    unsigned long long sharded_ns;                     // ... ns of those rounds in total (CTA 0 view)
+    unsigned long long sweep_ns[2];                    // in-situ bidding step of full-frontier rounds (nu == N): total ns / count
+    double tol;                                        // eps-CS tolerance of eCE_satisfied (1e-7, auction_.pyx:16; 0 in strict mode)
 };
 
 // Per-object record (32 B = one sector): everything a bidder needs to know about the object it wins, so that the
@@ -70,4 +75,15 @@ struct SslapbAuctionParams {
     int t_cluster;            // t_small < nu <= t_cluster -> the CTAs of cluster 0 run the rounds (0: regime off)
     int cluster;              // CTAs per cluster of the launch (1: no clusters)
     unsigned long long watchdog_ns;
+    // ---- row-sharded solve over several GPUs (instance of auction_sharded.cu; nranks == 1: off).  Persons are split into
+    // nnz-balanced contiguous row ranges; every rank holds the whole state and CSR, but in rounds with nu > t_shard it sweeps
+    // only the bidders of its own rows and stores their bids straight into EVERY rank's exchange buffer over NVLink.
+    int nranks, rank;
+    int t_shard;
+    const int *rowsplit;      // nranks + 1 row boundaries (device; written by sslapb_row_split_kernel)
+    const unsigned long long *xtab;   // per rank r: [3r] flag block, [3r+1] bidj[2][xcap], [3r+2] bidv[2][xcap] (peer-mapped addresses)
+    long long xcap;           // capacity (rows) of one parity half of the exchange buffers
+    unsigned xround_base;     // sharded rounds completed by earlier solves on this communicator (flags are monotone)
 };
+
+#define SSLAPB_MAX_RANKS 8

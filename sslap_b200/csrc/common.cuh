@@ -60,4 +60,10 @@ __device__ __forceinline__ SslapbRec256 sslapb_ld_rec256(const void *p)
     return r;
 }
 
+__device__ __forceinline__ void sslapb_st_rec256(void *p, unsigned long long start, unsigned long long owner_deg,
+                                                 unsigned long long price_bits)
+{
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" :: "l"(p), "l"(start), "l"(owner_deg), "l"(price_bits), "l"(0ull) : "memory");
+}
+
 #define SSLAPB_NEG_INF (__longlong_as_double((long long)0xfff0000000000000ull))

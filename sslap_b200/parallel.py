@@ -1,11 +1,42 @@
 """Host-side multi-GPU plumbing (one process per GPU, torch.distributed for rendezvous only).
 
-The auction path shards in exactly one way today: INDEPENDENT PROBLEMS (a batch, or replicas of one instance) are dealt
-out to the ranks, every rank runs the whole device-resident solve on its own GPU, and nothing crosses NVLink on the
-data path — results are gathered once at the end ("replicas only").  `balanced_row_split` is the
-nnz-balanced contiguous row partition the single-problem row-sharded path will use.
+Two ways of using several GPUs:
+  * ONE problem, persons row-sharded: `init_row_sharding` builds the communicator of the C ABI (sslapb_comm_init /
+    _connect) — every rank then calls `auction_solve` with the same full problem and the ranks split the bidding step of
+    the large-frontier rounds, exchanging bids in-kernel over NVLink; results are bit-identical on every rank.
+  * INDEPENDENT problems (a batch): dealt out to the ranks, every rank solves its shard with the one-warp-per-problem
+    batch kernel, nothing crosses NVLink on the data path, results are gathered once (`solve_batch_sharded`).
+`balanced_row_split` is the numpy statement of the nnz-balanced row partition the device computes
+(sslapb_row_split_kernel) — tests compare the two.
 """
 import numpy as np
+
+
+def init_row_sharding(handle=None, capacity_rows: int = 1 << 20, group=None):
+    """Build the row-sharding communicator over the ranks of a torch.distributed process group (any backend: only the
+    128-byte export blobs travel through it).  Every rank must call this, then make identical `auction_solve` calls on
+    `handle`.  Returns (rank, world)."""
+    import torch.distributed as dist
+    from . import _native as nat
+    h = handle or nat.default_handle()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world > nat.COMM_MAX_RANKS:
+        raise ValueError(f"row sharding supports up to {nat.COMM_MAX_RANKS} ranks")
+    mine = h.comm_init(world, rank, capacity_rows)
+    box = [None] * world
+    dist.all_gather_object(box, mine, group=group)
+    h.comm_connect(box)
+    dist.barrier(group=group)                             # nobody solves before every rank has mapped its peers
+    return rank, world
+
+
+def connect_local(handles, capacity_rows: int):
+    """Same-process communicator over `handles` (one per GPU, or several on ONE GPU with option "max_ctas" so that their
+    persistent kernels are co-resident — the virtual-shard test).  The solves must then run concurrently, one thread per
+    handle, because every sharded round waits for all ranks."""
+    blobs = [h.comm_init(len(handles), r, capacity_rows) for r, h in enumerate(handles)]
+    for h in handles:
+        h.comm_connect(blobs)
 
 
 def shard_range(n_items: int, world: int, rank: int):

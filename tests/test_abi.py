@@ -44,6 +44,27 @@ def test_meta_struct_layout_matches_header():
     assert ctypes.sizeof(nat.Meta) % 8 == 0
 
 
+def test_integration_stub_matches_the_binding():
+    """The ctypes stub INTEGRATION.md shows a maintainer of the reference must describe the SAME struct as the header and
+    the package's own binding (round 1 shipped a stub that was one field short: the library would have overrun it)."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"class Meta\(C\.Structure\):.*?_fields_ = \[(.*?)\]\n", text, flags=re.S).group(1)
+    fields = re.findall(r'\("([A-Za-z0-9_]+)",\s*C\.(c_[a-z0-9]+)(?:\s*\*\s*(\d+))?\)', block)
+    got = [(name, getattr(ctypes, ct) * int(n) if n else getattr(ctypes, ct)) for name, ct, n in fields]
+    assert [g[0] for g in got] == [f[0] for f in nat.Meta._fields_]
+    for (name, ct), (_, want) in zip(got, nat.Meta._fields_):
+        assert ctypes.sizeof(ct) == ctypes.sizeof(want) and getattr(ct, "_type_", ct) == getattr(want, "_type_", want), name
+    assert "sslapb_meta_size" in text and "sslapb_abi_version" in text
+    lib = ctypes.CDLL(nat.LIB_PATH)
+    lib.sslapb_meta_size.restype = ctypes.c_size_t
+    assert lib.sslapb_meta_size() == ctypes.sizeof(nat.Meta)
+    assert lib.sslapb_abi_version() == nat.ABI_VERSION
+    n_syms = int(re.search(r"\((\d+) `extern \"C\"` symbols", text).group(1))
+    assert n_syms == len(declared_symbols()) == len(nat.EXPORTS)
+    design = open(os.path.join(ROOT, "DESIGN.md")).read()
+    assert f"{n_syms} `extern \"C\"` symbols" in design
+
+
 def test_signatures_mirror_the_reference():
     # /root/reference/sslap/auction_solve.py:6-8 and check_feasible.py:5
     p = inspect.signature(sslap_b200.auction_solve).parameters
