@@ -26,7 +26,7 @@ cudaError_t sslapb_launch_index_max(const void *, const void *, int, long long, 
 cudaError_t sslapb_launch_dense_count(const double *, int, int, long long *, SslapbBuildFlags *, int, cudaStream_t);
 cudaError_t sslapb_launch_dense_fill(const double *, int, int, int, const long long *, int *, double *,
                                      SslapbBuildFlags *, int, cudaStream_t);
-cudaError_t sslapb_launch_auction(const SslapbAuctionParams *, int, int, int, int, cudaStream_t);
+cudaError_t sslapb_launch_auction(const SslapbAuctionParams *, int, int, int, int, int, cudaStream_t);
 cudaError_t sslapb_launch_row_split(const long long *, int, int, int *, cudaStream_t);
 int sslapb_coop_row_entries();
 cudaError_t sslapb_auction_grid_size(int, int *);
@@ -35,6 +35,7 @@ cudaError_t sslapb_launch_bid_sweep(const SslapbAuctionParams *, const int *, in
 cudaError_t sslapb_launch_sweep_plan(const SslapbAuctionParams *, int, int *, cudaStream_t);
 cudaError_t sslapb_launch_bid_sweep_tma(const SslapbAuctionParams *, const int *, float, int, int, cudaStream_t);
 cudaError_t sslapb_launch_price_bounds(const SslapbAuctionParams *, cudaStream_t);
+cudaError_t sslapb_launch_bid_sweep2(const SslapbAuctionParams *, const int *, int, float, int, int, int, int, cudaStream_t);
 cudaError_t sslapb_hk_launch_greedy(const long long *, const int *, int, int *, int *, SslapbHkFlags *, int, cudaStream_t);
 cudaError_t sslapb_hk_launch_phase_init(int, int, const int *, int *, int *, int *, int *, SslapbHkFlags *, int, cudaStream_t);
 cudaError_t sslapb_hk_launch_bfs_level(const long long *, const int *, int, int, const int *, int *, int *, int *, int *,
@@ -104,6 +105,7 @@ struct sslapb_handle {
     int t_shard = 16384;           // row-sharded solves: rounds with more bidders than this are split over the ranks
     int max_ctas = 0;              // upper bound of the persistent kernel's grid (0: one CTA per SM)
     int strict = 0;                // strict-optimality stop rule (see the header)
+    int coop = 1;                  // 0: launch the row-sharded persistent kernel without the cooperative attribute (virtual ranks)
     // warm start: prices for the next solve (sslapb_set_prices)
     DevBuf warm;
     int warm_cols = 0;
@@ -202,6 +204,7 @@ extern "C" int sslapb_set_option(sslapb_handle *h, const char *name, int64_t val
     if (!strcmp(name, "t_shard")) { if (value < 0 || value > 0x7fffffff) return SSLAPB_E_BAD_ARG; h->t_shard = (int)value; return 0; }
     if (!strcmp(name, "max_ctas")) { if (value < 0 || value > 65535) return SSLAPB_E_BAD_ARG; h->max_ctas = (int)value; return 0; }
     if (!strcmp(name, "strict")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->strict = (int)value; return 0; }
+    if (!strcmp(name, "coop")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->coop = (int)value; return 0; }
     return fail(h, SSLAPB_E_BAD_ARG, std::string("unknown option ") + name);
 }
 
@@ -483,7 +486,7 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
     int grid = P.cluster > 1 ? h->cluster_grid : h->grid;
     if (h->max_ctas > 0 && h->max_ctas < grid) { grid = h->max_ctas; if (P.cluster > 1) { P.cluster = 1; P.t_cluster = 0; } }
     CK(cudaEventRecord(h->ev[3], h->stream));
-    CK(sslapb_launch_auction(&P, grid, P.cluster, long_rows, warm, h->stream));
+    CK(sslapb_launch_auction(&P, grid, P.cluster, long_rows, warm, h->coop, h->stream));
     CK(cudaEventRecord(h->ev[4], h->stream));
     int rs[SSLAPB_MAX_RANKS + 1] = {};
     if (sharded) CK(cudaMemcpyAsync(rs, h->rowsplit.p, sizeof rs, cudaMemcpyDeviceToHost, h->stream));
@@ -790,6 +793,12 @@ extern "C" int sslapb_bid_sweep(sslapb_handle *h, const double *prices, const in
     // bit 2 of `merge`: identity frontier through the streamed (TMA ring) sweep, sweep_tma.cu — bit-identical results,
     // measured slower than the per-row kernel on B200, kept for A/B runs
     const bool streamed = !d_bidders && nb == h->N && (merge & 4);
+    // bit 3: the round-1 per-row kernel (one row per warp at a time) instead of the software-pipelined sweep (sweep2.cu,
+    // the default); bits 4-5: CTA size of the pipelined sweep for A/B runs (0: 768, 1: 1024, 2: 640, 3: 512 threads)
+    const bool legacy = (merge & 8) != 0;
+    static const int sw2_threads[4] = {768, 1024, 640, 512};
+    const int threads2 = sw2_threads[(merge >> 4) & 3];
+    const int lean2 = (merge & 64) ? 0 : 1;                    // bit 6: the untrimmed stage C (A/B)
     merge &= 3;
     if (streamed) {
         CK(h->sweep_plan.reserve(((size_t)h->sms + 2) * 4));
@@ -803,7 +812,8 @@ extern "C" int sslapb_bid_sweep(sslapb_handle *h, const double *prices, const in
         if (flush_l2) CK(cudaMemsetAsync(h->flush.p, it & 0xff, flush_bytes, h->stream));
         CK(cudaEventRecord(h->ev[3], h->stream));
         if (streamed) CK(sslapb_launch_bid_sweep_tma(&P, h->sweep_plan.as<int>(), eps, merge, h->sms, h->stream));
-        else CK(sslapb_launch_bid_sweep(&P, d_bidders, nb, eps, merge, h->sms, h->stream));
+        else if (legacy) CK(sslapb_launch_bid_sweep(&P, d_bidders, nb, eps, merge, h->sms, h->stream));
+        else CK(sslapb_launch_bid_sweep2(&P, d_bidders, nb, eps, merge, threads2, lean2, h->sms, h->stream));
         CK(cudaEventRecord(h->ev[4], h->stream));
         CK(cudaStreamSynchronize(h->stream));
         float ms = 0.f;

@@ -1416,7 +1416,11 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
 }
 
 // Cooperative launch of this translation unit's kernel instance, in thread-block clusters of `cluster` CTAs when > 1.
-static cudaError_t launch_persistent(const SslapbAuctionParams *P, int grid, int cluster, cudaStream_t stream)
+// coop = 0: an ordinary launch.  The driver runs one cooperative kernel at a time, so several persistent kernels that must
+// make progress TOGETHER on one GPU (the virtual-rank test of the row-sharded solve: K kernels of sms/K CTAs each, one CTA
+// per SM by construction) are launched without the cooperative attribute; co-residency then rests on grid <= free SMs, and
+// the barrier watchdog turns a violation into an error instead of a hang.
+static cudaError_t launch_persistent(const SslapbAuctionParams *P, int grid, int cluster, cudaStream_t stream, int coop = 1)
 {
     void *args[] = {(void *)P};
     cudaLaunchConfig_t cfg = {};
@@ -1426,6 +1430,7 @@ static cudaError_t launch_persistent(const SslapbAuctionParams *P, int grid, int
     at[1].id = cudaLaunchAttributeClusterDimension;
     at[1].val.clusterDim.x = cluster; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = cluster > 1 ? 2 : 1;
+    if (!coop) { cfg.attrs = nullptr; cfg.numAttrs = 0; }
     return cudaLaunchKernelExC(&cfg, (const void *)sslapb_auction_kernel, args);
 }
 #if defined(SSLAPB_LONG_ROWS)
@@ -1436,9 +1441,9 @@ extern "C" cudaError_t sslapb_launch_auction_long(const SslapbAuctionParams *P, 
 }
 extern "C" int sslapb_coop_row_entries() { return 4 * SSLAPB_COOP_CHUNKS - 3; }
 #elif defined(SSLAPB_SHARDED)
-extern "C" cudaError_t sslapb_launch_auction_sharded(const SslapbAuctionParams *P, int grid, cudaStream_t stream)
+extern "C" cudaError_t sslapb_launch_auction_sharded(const SslapbAuctionParams *P, int grid, int coop, cudaStream_t stream)
 {
-    return launch_persistent(P, grid, 1, stream);
+    return launch_persistent(P, grid, 1, stream, coop);
 }
 // nnz-balanced contiguous row split (the device-side counterpart of cumulative_idxs' row partition, auction_.pyx:33-48):
 // boundary r = first row whose CSR offset reaches r * nnz / parts (binary search over rowptr, one thread per boundary).
@@ -1564,12 +1569,13 @@ extern "C" cudaError_t sslapb_launch_auction_long(const SslapbAuctionParams *P, 
 extern "C" cudaError_t sslapb_launch_auction_cluster(const SslapbAuctionParams *P, int grid, int cluster, cudaStream_t stream);
 // Three instances of the persistent kernel: this one (lean), auction_long.cu (the longest row exceeds
 // sslapb_coop_row_entries() entries) and auction_cluster.cu (opt-in cluster regime, cluster > 1).
-extern "C" cudaError_t sslapb_launch_auction_sharded(const SslapbAuctionParams *P, int grid, cudaStream_t stream);
-extern "C" cudaError_t sslapb_launch_auction(const SslapbAuctionParams *P, int grid, int cluster, int long_rows, int warm, cudaStream_t stream)
+extern "C" cudaError_t sslapb_launch_auction_sharded(const SslapbAuctionParams *P, int grid, int coop, cudaStream_t stream);
+extern "C" cudaError_t sslapb_launch_auction(const SslapbAuctionParams *P, int grid, int cluster, int long_rows, int warm, int coop,
+                                             cudaStream_t stream)
 {
     sslapb_auction_init_kernel<<<grid, 1024, 0, stream>>>(*P, warm);
     if (long_rows) return sslapb_launch_auction_long(P, grid, stream);
-    if (P->nranks > 1) return sslapb_launch_auction_sharded(P, grid, stream);
+    if (P->nranks > 1) return sslapb_launch_auction_sharded(P, grid, coop, stream);
     if (cluster > 1) return sslapb_launch_auction_cluster(P, grid, cluster, stream);
     return launch_persistent(P, grid, 1, stream);
 }

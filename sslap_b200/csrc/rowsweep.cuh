@@ -257,6 +257,57 @@ __device__ __forceinline__ SslapbBid row_bid_pruned(const SslapbStreamChunk &C, 
     return o;
 }
 
+// Same function as row_bid_pruned with fewer instructions on the per-lane path (used by the pipelined sweep, sweep2.cu):
+//   * the in-row test is folded into the gather predicate (DSETP.AND) instead of substituting -inf for absent slots first;
+//   * -0.0 is folded into +0.0 by one addition of +0.0 (exact, IEEE: -0 + +0 = +0) instead of compare + selects;
+//   * the winning slot is always a gathered, hence in-row, slot: no second range test.
+__device__ __forceinline__ SslapbBid row_bid_pruned_lean(const SslapbStreamChunk &C, const double *price, long long start,
+                                                         int deg, int lane, double eps, double pmin, double thr,
+                                                         int &second_pass)
+{
+    const int off = 4 * lane - (int)(start & 3);              // row index of slot 0 (may be negative)
+    const int4 cj = C.cj;
+    const bool g0 = ((unsigned)off < (unsigned)deg) && (C.va.x >= thr);
+    const bool g1 = ((unsigned)(off + 1) < (unsigned)deg) && (C.va.y >= thr);
+    const bool g2 = ((unsigned)(off + 2) < (unsigned)deg) && (C.vb.x >= thr);
+    const bool g3 = ((unsigned)(off + 3) < (unsigned)deg) && (C.vb.y >= thr);
+    double v0 = SSLAPB_NEG_INF, v1 = SSLAPB_NEG_INF, v2 = SSLAPB_NEG_INF, v3 = SSLAPB_NEG_INF;
+    if (g0) v0 = C.va.x - price[cj.x];
+    if (g1) v1 = C.va.y - price[cj.y];
+    if (g2) v2 = C.vb.x - price[cj.z];
+    if (g3) v3 = C.vb.y - price[cj.w];
+    const SslapbLaneTop lt = sslapb_lane_top2(v0, v1, v2, v3);
+    const bool has = lt.b > SSLAPB_NEG_INF;
+    const int bi = has ? off + lt.w : -1;
+    const unsigned long long bk = has ? sslapb_ord64(lt.b + 0.0) : 0ull;
+    const unsigned long long sk = has ? sslapb_ord64(lt.s + 0.0) : 0ull;
+    const unsigned bh = (unsigned)(bk >> 32), bl = (unsigned)bk;
+    const unsigned khi = __reduce_max_sync(SSLAPB_FULL, bh);
+    const unsigned klo = __reduce_max_sync(SSLAPB_FULL, bh == khi ? bl : 0u);
+    const bool top = (bh == khi) & (bl == klo);
+    const int widx = __reduce_max_sync(SSLAPB_FULL, top ? bi : -1);
+    const bool iswin = top & (bi == widx) & has;
+    const unsigned long long cand = iswin ? sk : bk;
+    const unsigned chh = (unsigned)(cand >> 32), chl = (unsigned)cand;
+    const unsigned shi = __reduce_max_sync(SSLAPB_FULL, chh);
+    const unsigned slo = __reduce_max_sync(SSLAPB_FULL, chh == shi ? chl : 0u);
+    const unsigned long long skey = ((unsigned long long)shi << 32) | slo;
+    const unsigned own = __ballot_sync(SSLAPB_FULL, iswin);
+    const int src = own ? (__ffs(own) - 1) : lane;
+    const double myc = (lt.w & 2) ? ((lt.w & 1) ? C.vb.y : C.vb.x) : ((lt.w & 1) ? C.va.y : C.va.x);
+    const int myj = (lt.w & 2) ? ((lt.w & 1) ? cj.w : cj.z) : ((lt.w & 1) ? cj.y : cj.x);
+    const double bc = __shfl_sync(SSLAPB_FULL, myc, src);
+    const int bj = __shfl_sync(SSLAPB_FULL, myj, src);
+    const double wi = skey > SSLAPB_KEY_NEG_INF ? sslapb_key2double(skey) : SSLAPB_NEG_INF;   // :344
+    SslapbBid o;
+    o.powner = -1; o.pdeg = 0; o.pstart = 0;
+    o.bid = (bc - wi) + eps;                                   // :360
+    const bool proven = !(thr > SSLAPB_NEG_INF) || ((thr - pmin) < wi);
+    if (!proven) ++second_pass;
+    o.j = (own && proven) ? bj : -1;
+    return o;
+}
+
 template <int W>
 __device__ __forceinline__ void row_bid(const int *__restrict__ cols, const double *__restrict__ vals,
                                         const double *price, long long start, long long end, int t, double eps,

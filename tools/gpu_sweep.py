@@ -1,16 +1,28 @@
-"""Stand-alone sweep experiments on C3 with final prices: python tools/gpu_sweep.py"""
-import sys, os, time
+"""A/B of the full-frontier bidding sweep on C3 (final prices, L2 flushed before every launch): the software-pipelined kernel
+(default) in its CTA sizes, with the trimmed / untrimmed stage C, against the round-1 per-row kernel and the TMA ring.
+python tools/gpu_sweep.py [iters]     -> one line per variant: us per launch, GB/s, fraction of the measured copy peak"""
+import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, ctypes as C
 import sslap_b200
 from sslap_b200 import _native as nat
 from sslap_b200.datagen import make_problem
 h = nat.default_handle(); L = nat.load()
+iters = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+peak = 6455.6
+try:
+    peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
 n = 100000
 loc, val = make_problem(n, 0.001, "float", seed=0)
 sslap_b200.auction_solve(loc=loc, val=val, size=(n, n), cardinality_check=False)
-by = lambda nb: 12 * val.size * nb / n + 36 * nb
-for (nb, merge, flush) in [(n, 1, 1), (n, 0, 1), (n, 3, 1), (n // 2, 1, 1), (n // 4, 1, 1), (n, 1, 0)]:
-    ms = C.c_float(0)
-    rc = L.sslapb_bid_sweep(h.ptr, None, None, nb, 1e-5, merge, 10, flush, None, None, C.byref(ms))
-    print(f"nb={nb} merge={merge} flush={flush}: {ms.value*1e3:.1f} us  {by(nb)/ms.value/1e6:.0f} GB/s", flush=True)
+by = 12 * val.size + 36 * n
+variants = [("pipelined 768 thr (default)", 1), ("pipelined 1024 thr", 1 | 16), ("pipelined 640 thr", 1 | 32), ("pipelined 512 thr", 1 | 48),
+            ("pipelined 768 thr, untrimmed stage C", 1 | 64), ("pipelined 768 thr, pruning off", 3),
+            ("round-1 per-row kernel", 1 | 8), ("round-1 per-row kernel, pruning off", 3 | 8), ("TMA ring", 1 | 4)]
+for rep in range(2):
+    for name, merge in variants:
+        ms = C.c_float(0)
+        rc = L.sslapb_bid_sweep(h.ptr, None, None, n, 1e-5, merge, iters, 1, None, None, C.byref(ms))
+        print(f"rep{rep} {name:42s} rc={rc} {ms.value*1e3:7.1f} us  {by/ms.value/1e6:7.0f} GB/s  frac={by/ms.value/1e6/peak:.3f}", flush=True)
