@@ -95,6 +95,8 @@ int    sslapb_abi_version(void);
    default — opt-in, honoured only while t_small is 32), "watchdog_ms" (device watchdog of a single barrier wait, default 120000),
    "t_shard" (row-sharded solves: rounds with more bidders than this are split over the ranks; default 16384),
    "max_ctas" (upper bound of the persistent kernel's grid, 0 = one CTA per SM; used to co-schedule several solves on one GPU),
+   "hk_host_loop" (1: Hopcroft-Karp phases driven from the host with one read-back per BFS level, as in round 1, instead of the
+   device-resident loop; A/B runs; default 0),
    "coop" (row-sharded solves only; 0: launch the persistent kernel without the cooperative attribute so that several of them
    can run side by side on ONE GPU — the driver runs one cooperative kernel at a time; only for the virtual-rank test, default 1),
    "strict" (1: strict-optimality stop rule — eps-CS is tested with eps = 1/(N+1) and zero tolerance and the eps schedule runs
@@ -188,8 +190,9 @@ int sslapb_comm_destroy(sslapb_handle *h);
  *   prices (n_cols, host, NULL = keep the handle's current prices), bidders (nb int32, host, NULL = persons 0..nb-1)
  *   merge bit 0: also perform the per-object atomicMax of the bids (:375-385); bit 1: disable the bound pruning of
  *   the price gathers (A/B measurement); bit 2 (only with bidders == NULL, nb == n_rows): the streamed TMA-ring variant
- *   of the sweep (same results); bit 3: the round-1 per-row kernel instead of the default software-pipelined one (same
- *   results); bits 4-5: CTA size of the pipelined kernel (A/B runs);  iters >= 1 timed launches, with an L2
+ *   of the sweep; bit 7: the per-row kernel (one warp per row); bit 3: the software-pipelined per-row kernel (bits 4-6: its
+ *   CTA size / untrimmed stage); default: four rows per warp, 8 lanes per row — all variants return identical results
+ *   and exist for A/B measurement;  iters >= 1 timed launches, with an L2
  *   flush (a write larger than L2) before each when flush_l2 != 0.
  *   jbest_out / bid_out (nb, host, may be NULL); *avg_ms_out = mean device time of one launch (CUDA events).
  */

@@ -11,6 +11,9 @@
 #include <vector>
 #include <chrono>
 #include <mutex>
+#include <condition_variable>
+#include <map>
+#include <memory>
 #include <unistd.h>
 
 // ---- kernels' launchers (csr_build.cu / auction.cu / hopcroft.cu)
@@ -26,7 +29,8 @@ cudaError_t sslapb_launch_index_max(const void *, const void *, int, long long, 
 cudaError_t sslapb_launch_dense_count(const double *, int, int, long long *, SslapbBuildFlags *, int, cudaStream_t);
 cudaError_t sslapb_launch_dense_fill(const double *, int, int, int, const long long *, int *, double *,
                                      SslapbBuildFlags *, int, cudaStream_t);
-cudaError_t sslapb_launch_auction(const SslapbAuctionParams *, int, int, int, int, int, cudaStream_t);
+cudaError_t sslapb_launch_auction_init(const SslapbAuctionParams *, int, int, cudaStream_t);
+cudaError_t sslapb_launch_auction(const SslapbAuctionParams *, int, int, int, int, cudaStream_t);
 cudaError_t sslapb_launch_row_split(const long long *, int, int, int *, cudaStream_t);
 int sslapb_coop_row_entries();
 cudaError_t sslapb_auction_grid_size(int, int *);
@@ -36,11 +40,15 @@ cudaError_t sslapb_launch_sweep_plan(const SslapbAuctionParams *, int, int *, cu
 cudaError_t sslapb_launch_bid_sweep_tma(const SslapbAuctionParams *, const int *, float, int, int, cudaStream_t);
 cudaError_t sslapb_launch_price_bounds(const SslapbAuctionParams *, cudaStream_t);
 cudaError_t sslapb_launch_bid_sweep2(const SslapbAuctionParams *, const int *, int, float, int, int, int, int, cudaStream_t);
+cudaError_t sslapb_launch_bid_sweep4(const SslapbAuctionParams *, const int *, int, float, int, int, cudaStream_t);
 cudaError_t sslapb_hk_launch_greedy(const long long *, const int *, int, int *, int *, SslapbHkFlags *, int, cudaStream_t);
 cudaError_t sslapb_hk_launch_phase_init(int, int, const int *, int *, int *, int *, int *, SslapbHkFlags *, int, cudaStream_t);
 cudaError_t sslapb_hk_launch_bfs_level(const long long *, const int *, int, int, const int *, int *, int *, int *, int *,
                                        SslapbHkFlags *, int, cudaStream_t);
 cudaError_t sslapb_hk_launch_augment(int, const int *, const int *, int *, int *, SslapbHkFlags *, int, cudaStream_t);
+cudaError_t sslapb_hk_persistent_grid(int, int *);
+cudaError_t sslapb_hk_launch_persistent(const long long *, const int *, int, int, int *, int *, int *, int *, int *, int *, int *,
+                                        int *, int *, void *, int, cudaStream_t);
 }
 
 struct SslapbBatchMeta {
@@ -67,6 +75,29 @@ cudaError_t sslapb_launch_auction_batch(const SslapbBatchParams *, cudaStream_t)
 }
 
 namespace {
+
+// Launch gate of a communicator whose ranks all live in THIS process (several handles driven by threads, e.g. the
+// virtual-rank test on one GPU): every rank finishes its allocations, memsets, copies and set-up kernels, then waits here,
+// and only then launches its persistent kernel.  Device memory allocation / memset between two launches implicitly
+// serialises streams of one device, and a rank that is still allocating while another rank's kernel already waits for
+// its bids would deadlock until the watchdog.
+struct LocalGate {
+    std::mutex m;
+    std::condition_variable cv;
+    int n = 0, arrived = 0;
+    unsigned long long gen = 0;
+    bool arrive_and_wait(long long timeout_ms)
+    {
+        std::unique_lock<std::mutex> lk(m);
+        const unsigned long long g0 = gen;
+        if (++arrived == n) { arrived = 0; ++gen; cv.notify_all(); return true; }
+        if (cv.wait_for(lk, std::chrono::milliseconds(timeout_ms), [&] { return gen != g0; })) return true;
+        --arrived;
+        return false;
+    }
+};
+std::mutex g_gates_mu;
+std::map<unsigned long long, std::shared_ptr<LocalGate>> g_gates;
 
 struct DevBuf {
     void *p = nullptr;
@@ -117,6 +148,8 @@ struct sslapb_handle {
     void *peer_base[8] = {};       // peer-mapped base address of every rank's exchange buffer
     bool peer_ipc[8] = {};         // opened with cudaIpcOpenMemHandle (to be closed)
     unsigned xround = 0;           // sharded rounds completed on this communicator
+    std::shared_ptr<LocalGate> gate;   // all ranks in this process: rendezvous right before the persistent kernel's launch
+    unsigned long long gate_key = 0;
     // resident problem
     int N = 0, M = 0;
     int maxdeg = 0;                // longest row (read back after the row-maximum pass)
@@ -128,7 +161,10 @@ struct sslapb_handle {
     // auction state
     DevBuf price, owner, p2o, list, mover, bidj, bidv, bidkey, winpos, hole_count, chosen, ctrl, bidders, flush, sweep_plan;
     // HK state
-    DevBuf pair_u, pair_v, dist, visited, cursor, pred, hkflags;
+    DevBuf pair_u, pair_v, dist, visited, cursor, pred, hkflags, hkq;
+    int hk_grid = 0;
+    int hk_host_loop = 0;          // option "hk_host_loop": 1 = round 1's host-driven phase loop (A/B runs)
+    int hk_phases = 0, hk_levels = 0;   // instrumentation of the last run
 };
 
 #define CK(call)                                                                                         \
@@ -167,6 +203,7 @@ extern "C" int sslapb_create(int device, sslapb_handle **out)
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     if ((e = sslapb_auction_grid_size(device, &h->grid)) != cudaSuccess) { delete h; return -(int)e; }
     if ((e = sslapb_auction_cluster_grid(device, &h->cluster_grid, &h->cluster)) != cudaSuccess) { delete h; return -(int)e; }
+    if ((e = sslapb_hk_persistent_grid(device, &h->hk_grid)) != cudaSuccess) { delete h; return -(int)e; }
     *out = h;
     return SSLAPB_OK;
 }
@@ -179,7 +216,7 @@ extern "C" void sslapb_destroy(sslapb_handle *h)
     DevBuf *all[] = {&h->b_off, &h->b_rows, &h->b_cols, &h->b_eps, &h->b_meta, &h->b_bad, &h->sort_keys, &h->sort_idx, &h->sort_hist, &h->sort_rows, &h->sort_cols, &h->sort_val, &h->stage_idx, &h->stage_val, &h->stage_mat, &h->cols, &h->vals, &h->rowptr, &h->rowmax, &h->flags, &h->price,
                      &h->owner, &h->p2o, &h->list, &h->mover, &h->bidj, &h->bidv, &h->bidkey, &h->winpos,
                      &h->hole_count, &h->chosen, &h->ctrl, &h->bidders, &h->flush, &h->sweep_plan, &h->pair_u, &h->pair_v, &h->dist,
-                     &h->visited, &h->cursor, &h->pred, &h->hkflags};
+                     &h->visited, &h->cursor, &h->pred, &h->hkflags, &h->hkq};
     for (DevBuf *b : all) b->release();
     for (int r = 0; r < 8; ++r) if (h->peer_ipc[r] && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
     h->xbuf.release(); h->xtab.release(); h->rowsplit.release(); h->warm.release();
@@ -204,6 +241,7 @@ extern "C" int sslapb_set_option(sslapb_handle *h, const char *name, int64_t val
     if (!strcmp(name, "t_shard")) { if (value < 0 || value > 0x7fffffff) return SSLAPB_E_BAD_ARG; h->t_shard = (int)value; return 0; }
     if (!strcmp(name, "max_ctas")) { if (value < 0 || value > 65535) return SSLAPB_E_BAD_ARG; h->max_ctas = (int)value; return 0; }
     if (!strcmp(name, "strict")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->strict = (int)value; return 0; }
+    if (!strcmp(name, "hk_host_loop")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->hk_host_loop = (int)value; return 0; }
     if (!strcmp(name, "coop")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->coop = (int)value; return 0; }
     return fail(h, SSLAPB_E_BAD_ARG, std::string("unknown option ") + name);
 }
@@ -364,13 +402,30 @@ static int run_hopcroft(sslapb_handle *h, int32_t *card_out)
     CK(h->pair_u.reserve((size_t)N * 4)); CK(h->pair_v.reserve((size_t)M * 4));
     CK(h->dist.reserve((size_t)N * 4)); CK(h->visited.reserve((size_t)M * 4));      // visited = pred_v
     CK(h->cursor.reserve((size_t)N * 8)); CK(h->pred.reserve((size_t)N * 4));         // cursor = root | end_of_root
-    CK(h->hkflags.reserve(sizeof(SslapbHkFlags)));
+    CK(h->hkflags.reserve(sizeof(SslapbHkFlags) > sizeof(SslapbHkCtrl) ? sizeof(SslapbHkFlags) : sizeof(SslapbHkCtrl)));
     const long long *rowptr = h->rowptr.as<long long>();
     const int *cols = h->cols.as<int>();
     SslapbHkFlags *dF = h->hkflags.as<SslapbHkFlags>();
     int *root = h->cursor.as<int>(), *end_of_root = h->cursor.as<int>() + N, *pred_v = h->visited.as<int>();
     CK(cudaMemsetAsync(h->pair_u.p, 0xff, (size_t)N * 4, h->stream));
     CK(cudaMemsetAsync(h->pair_v.p, 0xff, (size_t)M * 4, h->stream));
+    if (!h->hk_host_loop) {
+        // device-resident phase loop: ONE cooperative launch, one read-back (feasibility_.pyx:199-211)
+        CK(h->hkq.reserve((size_t)N * 8));
+        SslapbHkCtrl hc;
+        memset(&hc, 0, sizeof hc);
+        CK(cudaMemcpyAsync(dF, &hc, sizeof hc, cudaMemcpyHostToDevice, h->stream));
+        CK(sslapb_hk_launch_persistent(rowptr, cols, N, M, h->pair_u.as<int>(), h->pair_v.as<int>(), root, end_of_root, pred_v,
+                                       h->dist.as<int>(), h->pred.as<int>(), h->hkq.as<int>(), h->hkq.as<int>() + N, dF,
+                                       h->hk_grid, h->stream));
+        CK(cudaMemcpyAsync(&hc, dF, sizeof hc, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (hc.watchdog) return fail(h, SSLAPB_E_ABORTED, "Hopcroft-Karp: device watchdog fired");
+        h->hk_phases = hc.phases; h->hk_levels = hc.levels;
+        if (getenv("SSLAPB_HK_TRACE")) fprintf(stderr, "hk persistent: matched=%d phases=%d levels=%d\n", hc.matched, hc.phases, hc.levels);
+        *card_out = (int32_t)hc.matched;
+        return SSLAPB_OK;
+    }
     CK(cudaMemsetAsync(dF, 0, sizeof(SslapbHkFlags), h->stream));
     CK(sslapb_hk_launch_greedy(rowptr, cols, N, h->pair_u.as<int>(), h->pair_v.as<int>(), dF, h->sms, h->stream));
     SslapbHkFlags F;
@@ -486,7 +541,15 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
     int grid = P.cluster > 1 ? h->cluster_grid : h->grid;
     if (h->max_ctas > 0 && h->max_ctas < grid) { grid = h->max_ctas; if (P.cluster > 1) { P.cluster = 1; P.t_cluster = 0; } }
     CK(cudaEventRecord(h->ev[3], h->stream));
-    CK(sslapb_launch_auction(&P, grid, P.cluster, long_rows, warm, h->coop, h->stream));
+    CK(sslapb_launch_auction_init(&P, grid, warm ? 1 : 0, h->stream));
+    if (sharded && h->gate) {                                  // in-process ranks: nobody launches before everybody is ready
+        CK(cudaStreamSynchronize(h->stream));
+        if (!h->gate->arrive_and_wait(h->watchdog_ms)) {
+            h->comm_broken = true;
+            return fail(h, SSLAPB_E_ABORTED, "a rank of this process did not reach the launch of the row-sharded solve");
+        }
+    }
+    CK(sslapb_launch_auction(&P, grid, P.cluster, long_rows, h->coop, h->stream));
     CK(cudaEventRecord(h->ev[4], h->stream));
     int rs[SSLAPB_MAX_RANKS + 1] = {};
     if (sharded) CK(cudaMemcpyAsync(rs, h->rowsplit.p, sizeof rs, cudaMemcpyDeviceToHost, h->stream));
@@ -701,6 +764,12 @@ extern "C" int sslapb_comm_destroy(sslapb_handle *h)
         h->peer_ipc[r] = false; h->peer_base[r] = nullptr;
     }
     h->xbuf.release(); h->xtab.release();
+    if (h->gate) {
+        std::lock_guard<std::mutex> g(g_gates_mu);
+        h->gate.reset();
+        auto it = g_gates.find(h->gate_key);
+        if (it != g_gates.end() && it->second.use_count() == 1) g_gates.erase(it);
+    }
     h->n_ranks = 1; h->rank = 0; h->comm_connected = false; h->comm_broken = false; h->xcap = 0; h->xround = 0;
     return SSLAPB_OK;
 }
@@ -760,6 +829,15 @@ extern "C" int sslapb_comm_connect(sslapb_handle *h, const void *all_exports)
         tab[3 * r + 2] = (unsigned long long)(b + 128);                                // bidv[2][xcap]
         tab[3 * r + 1] = (unsigned long long)(b + 128 + (size_t)h->xcap * 2 * 8);      // bidj[2][xcap]
     }
+    bool all_local = h->n_ranks > 1;
+    for (int r = 0; r < h->n_ranks; ++r) all_local = all_local && E[r].pid == (long long)getpid();
+    if (all_local) {
+        std::lock_guard<std::mutex> g(g_gates_mu);
+        h->gate_key = E[0].base;
+        auto &slot = g_gates[h->gate_key];
+        if (!slot) { slot = std::make_shared<LocalGate>(); slot->n = h->n_ranks; }
+        h->gate = slot;
+    }
     CK(h->xtab.reserve(sizeof tab));
     CK(cudaMemcpyAsync(h->xtab.p, tab, sizeof tab, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -793,9 +871,11 @@ extern "C" int sslapb_bid_sweep(sslapb_handle *h, const double *prices, const in
     // bit 2 of `merge`: identity frontier through the streamed (TMA ring) sweep, sweep_tma.cu — bit-identical results,
     // measured slower than the per-row kernel on B200, kept for A/B runs
     const bool streamed = !d_bidders && nb == h->N && (merge & 4);
-    // bit 3: the round-1 per-row kernel (one row per warp at a time) instead of the software-pipelined sweep (sweep2.cu,
-    // the default); bits 4-5: CTA size of the pipelined sweep for A/B runs (0: 768, 1: 1024, 2: 640, 3: 512 threads)
-    const bool legacy = (merge & 8) != 0;
+    // variants of the sweep, all bit-identical (A/B runs): bit 7 = the per-row kernel (one warp per row, 32
+    // warps per SM); bit 3 = the software-pipelined per-row kernel (sweep2.cu; bits 4-5: its CTA size 768 / 1024 / 640 / 512,
+    // bit 6: untrimmed stage C); default = four rows per warp, 8 lanes per row (sweep4.cu)
+    const bool per_row = (merge & 128) != 0;
+    const bool pipelined = (merge & 8) != 0;
     static const int sw2_threads[4] = {768, 1024, 640, 512};
     const int threads2 = sw2_threads[(merge >> 4) & 3];
     const int lean2 = (merge & 64) ? 0 : 1;                    // bit 6: the untrimmed stage C (A/B)
@@ -812,8 +892,9 @@ extern "C" int sslapb_bid_sweep(sslapb_handle *h, const double *prices, const in
         if (flush_l2) CK(cudaMemsetAsync(h->flush.p, it & 0xff, flush_bytes, h->stream));
         CK(cudaEventRecord(h->ev[3], h->stream));
         if (streamed) CK(sslapb_launch_bid_sweep_tma(&P, h->sweep_plan.as<int>(), eps, merge, h->sms, h->stream));
-        else if (legacy) CK(sslapb_launch_bid_sweep(&P, d_bidders, nb, eps, merge, h->sms, h->stream));
-        else CK(sslapb_launch_bid_sweep2(&P, d_bidders, nb, eps, merge, threads2, lean2, h->sms, h->stream));
+        else if (per_row) CK(sslapb_launch_bid_sweep(&P, d_bidders, nb, eps, merge, h->sms, h->stream));
+        else if (pipelined) CK(sslapb_launch_bid_sweep2(&P, d_bidders, nb, eps, merge, threads2, lean2, h->sms, h->stream));
+        else CK(sslapb_launch_bid_sweep4(&P, d_bidders, nb, eps, merge, h->sms, h->stream));
         CK(cudaEventRecord(h->ev[4], h->stream));
         CK(cudaStreamSynchronize(h->stream));
         float ms = 0.f;

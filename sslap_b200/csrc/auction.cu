@@ -1570,10 +1570,14 @@ extern "C" cudaError_t sslapb_launch_auction_cluster(const SslapbAuctionParams *
 // Three instances of the persistent kernel: this one (lean), auction_long.cu (the longest row exceeds
 // sslapb_coop_row_entries() entries) and auction_cluster.cu (opt-in cluster regime, cluster > 1).
 extern "C" cudaError_t sslapb_launch_auction_sharded(const SslapbAuctionParams *P, int grid, int coop, cudaStream_t stream);
-extern "C" cudaError_t sslapb_launch_auction(const SslapbAuctionParams *P, int grid, int cluster, int long_rows, int warm, int coop,
-                                             cudaStream_t stream)
+extern "C" cudaError_t sslapb_launch_auction_init(const SslapbAuctionParams *P, int grid, int warm, cudaStream_t stream)
 {
     sslapb_auction_init_kernel<<<grid, 1024, 0, stream>>>(*P, warm);
+    return cudaGetLastError();
+}
+extern "C" cudaError_t sslapb_launch_auction(const SslapbAuctionParams *P, int grid, int cluster, int long_rows, int coop,
+                                             cudaStream_t stream)
+{
     if (long_rows) return sslapb_launch_auction_long(P, grid, stream);
     if (P->nranks > 1) return sslapb_launch_auction_sharded(P, grid, coop, stream);
     if (cluster > 1) return sslapb_launch_auction_cluster(P, grid, cluster, stream);

@@ -16,3 +16,15 @@ struct SslapbHkFlags {
     int augmented;    // successful augmentations in this phase
     int matched;      // greedy initial matches
 };
+
+// Control block of the device-resident Hopcroft-Karp loop (hopcroft.cu: sslapb_hk_persistent_kernel)
+struct SslapbHkCtrl {
+    unsigned bar;             // grid barrier: monotone arrival counter
+    int found;                // some tree reached a free right vertex in this phase
+    int cnt[3];               // frontier sizes, rotating by level (cnt[L % 3] = size of level L)
+    int nroots;               // free left vertices at the start of the phase
+    int augmented;            // (unused)
+    int matched;              // size of the matching
+    int phases, levels;       // instrumentation: phases run, BFS levels in total
+    int watchdog;             // 1: a barrier wait exceeded the limit
+};

@@ -229,3 +229,40 @@ def test_row_sharded_solve_with_virtual_ranks_on_one_gpu(gpu, oracle_mod, k_rank
     finally:
         for hh in handles:
             hh.close()
+
+
+def test_hopcroft_device_loop_matches_host_loop_and_scipy(gpu, oracle_mod):
+    """The device-resident Hopcroft-Karp phase loop (one cooperative launch, frontier queues) against round 1's host-driven
+    loop, the oracle and scipy: cardinality identical on deficient graphs that need many phases and long paths."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import maximum_bipartite_matching
+    from conftest import assert_valid_matching
+    sslap_b200, nat, h = gpu
+    rng = np.random.default_rng(31)
+    cases = [(100000, 100000, 300000), (5000, 7000, 9000), (7000, 5000, 30000), (300, 300, 310), (1, 1, 1), (50000, 50000, 60000)]
+    # a path graph: ONE augmenting path of maximal length after the greedy pass
+    n = 2000
+    chain = np.array([[i, i] for i in range(n)] + [[i, i + 1] for i in range(n - 1)], dtype=np.int32)
+    chain = chain[np.lexsort((chain[:, 1], chain[:, 0]))]
+    graphs = [chain[1:]]                                                    # drop (0,0): forces the long alternating path
+    for (n, m, e) in cases:
+        key = np.unique(rng.integers(0, n, e).astype(np.int64) * m + rng.integers(0, m, e))
+        graphs.append(np.stack([key // m, key % m], -1).astype(np.int32))
+    for loc in graphs:
+        n, m = int(loc[:, 0].max()) + 1, int(loc[:, 1].max()) + 1
+        g = sp.csr_matrix((np.ones(len(loc), dtype=np.int8), (loc[:, 0], loc[:, 1])), shape=(n, m))
+        card = int((maximum_bipartite_matching(g, perm_type="column") >= 0).sum())
+        sizes = []
+        for mode in (0, 1):
+            h.set_option("hk_host_loop", mode)
+            try:
+                r = sslap_b200.hopcroft_solve(loc=loc)
+            finally:
+                h.set_option("hk_host_loop", 0)
+            assert_valid_matching(r, loc) if len(loc) < 50000 else None
+            lp, rp = r["left_pairings"], r["right_pairings"]
+            assert int((lp >= 0).sum()) == r["size"] == int((rp >= 0).sum())
+            sizes.append(r["size"])
+        assert sizes == [card, card], (n, m, sizes, card)
+        if n <= 100000:
+            assert oracle_mod.hopcroft_solve(loc=loc)["size"] == card
