@@ -97,6 +97,7 @@ int    sslapb_abi_version(void);
    "max_ctas" (upper bound of the persistent kernel's grid, 0 = one CTA per SM; used to co-schedule several solves on one GPU),
    "hk_host_loop" (1: Hopcroft-Karp phases driven from the host with one read-back per BFS level, as in round 1, instead of the
    device-resident loop; A/B runs; default 0),
+   "batch_v1" (1: round 1's batch kernel — a whole warp sweeps one bidder at a time — instead of the sub-warp kernel; A/B runs),
    "coop" (row-sharded solves only; 0: launch the persistent kernel without the cooperative attribute so that several of them
    can run side by side on ONE GPU — the driver runs one cooperative kernel at a time; only for the virtual-rank test, default 1),
    "strict" (1: strict-optimality stop rule — eps-CS is tested with eps = 1/(N+1) and zero tolerance and the eps schedule runs

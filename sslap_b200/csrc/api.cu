@@ -51,27 +51,12 @@ cudaError_t sslapb_hk_launch_persistent(const long long *, const int *, int, int
                                         int *, int *, void *, int, cudaStream_t);
 }
 
-struct SslapbBatchMeta {
-    float start_eps, final_eps, target_eps;
-    int eCE, soln_found, stop_reason;
-    long long its, nreductions, n_assigned;
-};
-struct SslapbBatchParams {
-    int P;
-    const long long *rowoff, *coloff;
-    const long long *rowptr;
-    const int *cols;
-    const double *vals;
-    const float *eps_start;
-    long long max_iter;
-    double *price; int *owner; unsigned long long *bestkey; int *winpos;
-    int *p2o, *list, *mover, *bidj; double *bidv, *chosen;
-    SslapbBatchMeta *meta;
-};
+#include "batch.cuh"
 extern "C" {
 cudaError_t sslapb_launch_batch_globalize(const void *, const void *, int, long long, const long long *, const long long *,
                                           const long long *, int, int *, int *, int *, int, cudaStream_t);
 cudaError_t sslapb_launch_auction_batch(const SslapbBatchParams *, cudaStream_t);
+cudaError_t sslapb_launch_auction_batch2(const SslapbBatchParams *, cudaStream_t);
 }
 
 namespace {
@@ -157,7 +142,8 @@ struct sslapb_handle {
     bool has_vals = false;
     DevBuf stage_idx, stage_val, stage_mat, cols, vals, rowptr, rowmax, flags;
     DevBuf sort_keys, sort_idx, sort_hist, sort_rows, sort_cols, sort_val;   // only for unsorted input
-    DevBuf b_off, b_rows, b_cols, b_eps, b_meta, b_bad;                      // batched problems
+    DevBuf b_off, b_rows, b_cols, b_eps, b_meta, b_bad, b_rec;               // batched problems
+    int batch_v1 = 0;              // option "batch_v1": 1 = round 1's batch kernel (whole warp per bidder), A/B runs
     // auction state
     DevBuf price, owner, p2o, list, mover, bidj, bidv, bidkey, winpos, hole_count, chosen, ctrl, bidders, flush, sweep_plan;
     // HK state
@@ -213,7 +199,7 @@ extern "C" void sslapb_destroy(sslapb_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *all[] = {&h->b_off, &h->b_rows, &h->b_cols, &h->b_eps, &h->b_meta, &h->b_bad, &h->sort_keys, &h->sort_idx, &h->sort_hist, &h->sort_rows, &h->sort_cols, &h->sort_val, &h->stage_idx, &h->stage_val, &h->stage_mat, &h->cols, &h->vals, &h->rowptr, &h->rowmax, &h->flags, &h->price,
+    DevBuf *all[] = {&h->b_rec, &h->b_off, &h->b_rows, &h->b_cols, &h->b_eps, &h->b_meta, &h->b_bad, &h->sort_keys, &h->sort_idx, &h->sort_hist, &h->sort_rows, &h->sort_cols, &h->sort_val, &h->stage_idx, &h->stage_val, &h->stage_mat, &h->cols, &h->vals, &h->rowptr, &h->rowmax, &h->flags, &h->price,
                      &h->owner, &h->p2o, &h->list, &h->mover, &h->bidj, &h->bidv, &h->bidkey, &h->winpos,
                      &h->hole_count, &h->chosen, &h->ctrl, &h->bidders, &h->flush, &h->sweep_plan, &h->pair_u, &h->pair_v, &h->dist,
                      &h->visited, &h->cursor, &h->pred, &h->hkflags, &h->hkq};
@@ -242,6 +228,7 @@ extern "C" int sslapb_set_option(sslapb_handle *h, const char *name, int64_t val
     if (!strcmp(name, "max_ctas")) { if (value < 0 || value > 65535) return SSLAPB_E_BAD_ARG; h->max_ctas = (int)value; return 0; }
     if (!strcmp(name, "strict")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->strict = (int)value; return 0; }
     if (!strcmp(name, "hk_host_loop")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->hk_host_loop = (int)value; return 0; }
+    if (!strcmp(name, "batch_v1")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->batch_v1 = (int)value; return 0; }
     if (!strcmp(name, "coop")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->coop = (int)value; return 0; }
     return fail(h, SSLAPB_E_BAD_ARG, std::string("unknown option ") + name);
 }
@@ -571,6 +558,9 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
     }
     if (c.abort_flag) {
         std::string msg = c.abort_flag == 2 ? "empty row reached the bidding kernel" : "device watchdog fired";
+        if (sharded)
+            msg += " [rank " + std::to_string(h->rank) + "/" + std::to_string(h->n_ranks) + " nu=" + std::to_string(c.nu) + " its=" +
+                   std::to_string(c.its) + " sharded rounds=" + std::to_string(c.rounds_sharded) + " grid=" + std::to_string(grid) + "]";
         if (P.cluster > 1) {                                   // where the CTAs of cluster 0 were (barrier count per CTA)
             msg += " [nu=" + std::to_string(c.nu) + " its=" + std::to_string(c.its) + " cluster barriers:";
             for (int k = 0; k < P.cluster && k < 16; ++k) msg += " " + std::to_string(c.dbg[k]);
@@ -993,8 +983,11 @@ extern "C" int sslapb_auction_batch(sslapb_handle *h, int32_t n_problems, const 
     B.winpos = h->winpos.as<int>(); B.p2o = h->p2o.as<int>(); B.list = h->list.as<int>(); B.mover = h->mover.as<int>();
     B.bidj = h->bidj.as<int>(); B.bidv = h->bidv.as<double>(); B.chosen = h->chosen.as<double>();
     B.meta = h->b_meta.as<SslapbBatchMeta>();
+    CK(h->b_rec.reserve((size_t)Cn * sizeof(SslapbBatchRec)));
+    B.brec = h->b_rec.as<SslapbBatchRec>();
     CK(cudaEventRecord(h->ev[3], h->stream));
-    CK(sslapb_launch_auction_batch(&B, h->stream));
+    if (h->batch_v1) CK(sslapb_launch_auction_batch(&B, h->stream));
+    else CK(sslapb_launch_auction_batch2(&B, h->stream));
     CK(cudaEventRecord(h->ev[4], h->stream));
     std::vector<SslapbBatchMeta> bm((size_t)P);
     std::vector<double> chosen((size_t)R);

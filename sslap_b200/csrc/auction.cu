@@ -30,50 +30,6 @@
 #include "rowsweep.cuh"
 
 
-// eCE / objective sweep of one row by a full warp (auction_.pyx:460-483 and :504-521).
-//   vmax   = max_k (a_ik - p_k)
-//   choice = value of the LAST entry whose column is jsel (:467-471)
-//   csum   = sum of the values of ALL entries whose column is jsel (get_obj adds every match, :514-521)
-__device__ __forceinline__ void row_ece(const int *__restrict__ cols, const double *__restrict__ vals,
-                                        const double *price, long long start, long long end, int lane, int jsel,
-                                        double &vmax, double &choice, double &csum)
-{
-    const int4 *c4 = reinterpret_cast<const int4 *>(cols);
-    const double2 *v2 = reinterpret_cast<const double2 *>(vals);
-    double vm = SSLAPB_NEG_INF, ch_v = 0.0, cs = 0.0;
-    int ch_i = -1;
-    const long long c0 = start >> 2, c1 = (end + 3) >> 2;
-    const int trips = __shfl_sync(SSLAPB_FULL, (int)((c1 - c0 + 31) / 32), 0);
-    for (int it = 0; it < trips; ++it) {
-        const long long ch = c0 + (long long)it * 32 + lane;
-        if (ch >= c1) continue;
-        const int4 cj = sslapb_ldg_stream_i4(c4 + ch);
-        const double2 va = sslapb_ldg_stream_d2(v2 + 2 * ch);
-        const double2 vb = sslapb_ldg_stream_d2(v2 + 2 * ch + 1);
-        const long long e0 = ch << 2;
-        const int cc[4] = {cj.x, cj.y, cj.z, cj.w};
-        const double vv[4] = {va.x, va.y, vb.x, vb.y};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const long long e = e0 + k;
-            if (e >= start && e < end) {
-                const double v = vv[k] - price[cc[k]];
-                vm = fmax(vm, v);
-                if (cc[k] == jsel) { ch_v = vv[k]; ch_i = (int)(e - start); cs += vv[k]; }
-            }
-        }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        vm = fmax(vm, __shfl_xor_sync(SSLAPB_FULL, vm, off));
-        const int oi = __shfl_xor_sync(SSLAPB_FULL, ch_i, off);
-        const double ov = __shfl_xor_sync(SSLAPB_FULL, ch_v, off);
-        if (oi > ch_i) { ch_i = oi; ch_v = ov; }
-        cs += __shfl_xor_sync(SSLAPB_FULL, cs, off);
-    }
-    vmax = vm; choice = ch_v; csum = cs;
-}
-
 // ----------------------------------------------------------------------------------------------------------------------
 // Grid barrier: ONE release-add per CTA on a monotonically increasing counter, then acquire-polling of the same word
 // until it reaches `target` (= barriers passed so far * #CTAs; every CTA counts its barriers in a register, so there is
@@ -1639,24 +1595,7 @@ extern "C" cudaError_t sslapb_launch_bid_sweep(const SslapbAuctionParams *P, con
 // eps-CS test (:268-309, :443-485) — so `sol`, `its` and every meta key are bit-identical to a reference call per problem.
 // The problems are stored block-diagonally in ONE CSR (global row/column ids), built by the ordinary ingest pass.
 // ======================================================================================================================
-struct SslapbBatchMeta {
-    float start_eps, final_eps, target_eps;
-    int eCE, soln_found, stop_reason;
-    long long its, nreductions, n_assigned;
-};
-
-struct SslapbBatchParams {
-    int P;
-    const long long *rowoff, *coloff;     // P+1 prefix sums of the problems' row / column counts
-    const long long *rowptr;              // global CSR
-    const int *cols;                      // global column ids
-    const double *vals;                   // sign-folded
-    const float *eps_start;               // per problem, <= 0 => C/2 (nullable)
-    long long max_iter;
-    double *price; int *owner; unsigned long long *bestkey; int *winpos;      // per global column
-    int *p2o, *list, *mover, *bidj; double *bidv, *chosen;                    // per global row
-    SslapbBatchMeta *meta;
-};
+#include "batch.cuh"
 
 __device__ __forceinline__ bool batch_ece(const SslapbBatchParams &B, long long r0, int N, int lane, float teps)
 {

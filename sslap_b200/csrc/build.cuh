@@ -20,7 +20,7 @@ struct SslapbHkFlags {
 // Control block of the device-resident Hopcroft-Karp loop (hopcroft.cu: sslapb_hk_persistent_kernel)
 struct SslapbHkCtrl {
     unsigned bar;             // grid barrier: monotone arrival counter
-    int found;                // some tree reached a free right vertex in this phase
+    int found;                // 0, or 1 + the BFS level at which a tree reached a free right vertex in this phase
     int cnt[3];               // frontier sizes, rotating by level (cnt[L % 3] = size of level L)
     int nroots;               // free left vertices at the start of the phase
     int augmented;            // (unused)

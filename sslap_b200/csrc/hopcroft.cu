@@ -167,7 +167,7 @@ __device__ __forceinline__ bool hk_grid_barrier(SslapbHkCtrl *c, unsigned nblk, 
             if (polls == 4096) t0 = sslapb_globaltimer();
             if (sslapb_ld_volatile_s32(&c->watchdog)) { ab = 1; break; }
             __nanosleep(200);
-            if (sslapb_globaltimer() - t0 > 60000000000ull) { *(volatile int *)&c->watchdog = 1; ab = 1; break; }
+            if (sslapb_globaltimer() - t0 > 20000000000ull) { *(volatile int *)&c->watchdog = 1; ab = 1; break; }
         }
         s_ab = ab | sslapb_ld_volatile_s32(&c->watchdog);
     }
@@ -248,7 +248,9 @@ __global__ void __launch_bounds__(HK_THREADS, 2) sslapb_hk_persistent_kernel(con
                     if (atomicCAS(pred_v + v, -1, u) != -1) continue;      // somebody else's tree
                     const int pu = pair_v[v];
                     if (pu == -1) {                                        // free right vertex: endpoint of tree r (first wins)
-                        if (atomicCAS(end_of_root + r, -1, v) == -1) *(volatile int *)&C->found = 1;
+                        // `found` carries the level (+1): a CTA that is already one level ahead must not make a slower
+                        // CTA, which has not read the flag for the previous level yet, leave the loop one level early
+                        if (atomicCAS(end_of_root + r, -1, v) == -1) *(volatile int *)&C->found = level + 1;
                     } else {                                               // matched: its partner joins the next level of tree r
                         root[pu] = r;
                         qn[atomicAdd(cn, 1)] = pu;
@@ -256,7 +258,8 @@ __global__ void __launch_bounds__(HK_THREADS, 2) sslapb_hk_persistent_kernel(con
                 }
             }
             if (!hk_grid_barrier(C, nblk, epoch)) return;
-            found = *(volatile int *)&C->found;
+            const int fl = *(volatile int *)&C->found;
+            found = fl != 0 && fl <= level + 1;                // an endpoint was found at this level (or, impossible, an earlier one)
             const int nnext = *(volatile int *)cn;
             ++level;
             if (found || nnext == 0) break;

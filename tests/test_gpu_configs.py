@@ -189,7 +189,7 @@ def test_row_sharded_solve_with_virtual_ranks_on_one_gpu(gpu, oracle_mod, k_rank
     handles = [nat.Handle(0) for _ in range(k_ranks)]
     try:
         for hh in handles:
-            hh.set_option("max_ctas", max(1, sms // k_ranks))
+            hh.set_option("max_ctas", max(1, (sms - 4) // k_ranks))           # one CTA per SM: all K grids must be co-resident
             hh.set_option("coop", 0)                                         # the driver runs ONE cooperative kernel at a time
             hh.set_option("t_shard", 48)                                     # shard (almost) every grid round
             hh.set_option("watchdog_ms", 20000)

@@ -268,11 +268,16 @@ def test_batch_matches_single_problem_calls(gpu, oracle_mod):
         loc, val = make_problem(n, 0.05 if n == 512 else 0.2, mode, seed=100 + k)
         probs.append((loc, val, (n, n)))
         want.append(oracle_mod.auction_solve(loc=loc, val=val, problem="max"))
-    got = sslap_b200.auction_solve_batch(probs, problem="max")
-    assert len(got) == len(want)
-    for g, w in zip(got, want):
-        assert np.array_equal(g["sol"], w["sol"])
-        assert_meta_equal(g["meta"], w["meta"])
+    for v1 in (0, 1):                                     # the sub-warp kernel (default) and round 1's kernel
+        h.set_option("batch_v1", v1)
+        try:
+            got = sslap_b200.auction_solve_batch(probs, problem="max")
+        finally:
+            h.set_option("batch_v1", 0)
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert np.array_equal(g["sol"], w["sol"])
+            assert_meta_equal(g["meta"], w["meta"])
     # golden: the reference's own result for one 512 x 512 problem, run as a batch of copies
     gold = load_golden("c5_one")
     res = sslap_b200.auction_solve_batch([(gold["loc"], gold["val"], (512, 512))] * 5, problem=gold["problem"])
