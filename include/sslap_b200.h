@@ -66,10 +66,10 @@ typedef struct sslapb_meta {
     int64_t nnz;
     int64_t rounds_grid, rounds_warp, rounds_solo;   /* rounds executed per regime */
     float   prof_ms[8];      /* device time by section: grid bid, grid assign, grid compaction, warp regime, solo regime,
-                                eCE + phase change, cluster regime, grid barriers */
+                                eCE + phase change, (unused), grid barriers */
     int64_t prune_second_pass; /* grid-regime rows whose bound-pruned sweep needed the second (exactness) gather pass */
     int32_t stop_reason;     /* 1 target-eps CS holds (:275) | 2 eps < target (:280) | 3 max_iter (:309) */
-    int32_t rounds_cluster;  /* rounds run by cluster 0 alone (mid-sized frontiers); the others are in rounds_grid/warp/solo */
+    int32_t rounds_cluster;  /* always 0 (round 1's opt-in cluster regime was removed; the field keeps the layout) */
     /* ---- ABI version 2 ---- */
     int32_t n_ranks, rank;   /* row-sharded solve (sslapb_comm_init): size of the communicator and this handle's rank; 1, 0 otherwise */
     int32_t row_lo, row_hi;  /* ... the nnz-balanced row range [row_lo, row_hi) this rank bids for in sharded rounds */
@@ -90,9 +90,8 @@ const char *sslapb_last_error(const sslapb_handle *h);
    assert both before its first call (a shorter struct on the caller's side would be overrun by the library). */
 size_t sslapb_meta_size(void);
 int    sslapb_abi_version(void);
-/* tuning knobs: "t_small" (frontier size at or below which CTA 0 runs rounds alone, 0..32), "t_cluster" (frontier size
-   at or below which one thread-block cluster of 8 CTAs runs the rounds with hardware cluster barriers; 0 = off, the
-   default — opt-in, honoured only while t_small is 32), "watchdog_ms" (device watchdog of a single barrier wait, default 120000),
+/* tuning knobs (none changes results): "t_small" (frontier size at or below which CTA 0 runs rounds alone, 0..32),
+   "watchdog_ms" (device watchdog of a single barrier wait, default 120000),
    "t_shard" (row-sharded solves: rounds with more bidders than this are split over the ranks; default 16384),
    "max_ctas" (upper bound of the persistent kernel's grid, 0 = one CTA per SM; used to co-schedule several solves on one GPU),
    "hk_host_loop" (1: Hopcroft-Karp phases driven from the host with one read-back per BFS level, as in round 1, instead of the

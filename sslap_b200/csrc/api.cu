@@ -30,11 +30,10 @@ cudaError_t sslapb_launch_dense_count(const double *, int, int, long long *, Ssl
 cudaError_t sslapb_launch_dense_fill(const double *, int, int, int, const long long *, int *, double *,
                                      SslapbBuildFlags *, int, cudaStream_t);
 cudaError_t sslapb_launch_auction_init(const SslapbAuctionParams *, int, int, cudaStream_t);
-cudaError_t sslapb_launch_auction(const SslapbAuctionParams *, int, int, int, int, cudaStream_t);
+cudaError_t sslapb_launch_auction(const SslapbAuctionParams *, int, int, int, cudaStream_t);
 cudaError_t sslapb_launch_row_split(const long long *, int, int, int *, cudaStream_t);
 int sslapb_coop_row_entries();
 cudaError_t sslapb_auction_grid_size(int, int *);
-cudaError_t sslapb_auction_cluster_grid(int, int *, int *);
 cudaError_t sslapb_launch_bid_sweep(const SslapbAuctionParams *, const int *, int, float, int, int, cudaStream_t);
 cudaError_t sslapb_launch_sweep_plan(const SslapbAuctionParams *, int, int *, cudaStream_t);
 cudaError_t sslapb_launch_bid_sweep_tma(const SslapbAuctionParams *, const int *, float, int, int, cudaStream_t);
@@ -113,10 +112,6 @@ struct sslapb_handle {
     cudaEvent_t ev[6] = {};
     std::string err;
     int t_small = 32;
-    int t_cluster = 0;             // frontier size up to which cluster 0 runs the rounds alone; 0 = regime off (default):
-                                   // the launch is then the plain cooperative one, one CTA on every SM
-    int cluster = 1;               // CTAs per cluster the device supports for the persistent kernel (1: none)
-    int cluster_grid = 0;          // grid of the cluster launch (a multiple of `cluster`)
     long long watchdog_ms = 120000;
     int t_shard = 16384;           // row-sharded solves: rounds with more bidders than this are split over the ranks
     int max_ctas = 0;              // upper bound of the persistent kernel's grid (0: one CTA per SM)
@@ -188,7 +183,6 @@ extern "C" int sslapb_create(int device, sslapb_handle **out)
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete h; return -(int)e; }
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     if ((e = sslapb_auction_grid_size(device, &h->grid)) != cudaSuccess) { delete h; return -(int)e; }
-    if ((e = sslapb_auction_cluster_grid(device, &h->cluster_grid, &h->cluster)) != cudaSuccess) { delete h; return -(int)e; }
     if ((e = sslapb_hk_persistent_grid(device, &h->hk_grid)) != cudaSuccess) { delete h; return -(int)e; }
     *out = h;
     return SSLAPB_OK;
@@ -221,7 +215,6 @@ extern "C" int sslapb_set_option(sslapb_handle *h, const char *name, int64_t val
 {
     if (!h || !name) return SSLAPB_E_BAD_ARG;
     LOCK(h);
-    if (!strcmp(name, "t_cluster")) { if (value < 0 || value > (1 << 20)) return SSLAPB_E_BAD_ARG; h->t_cluster = (int)value; return 0; }
     if (!strcmp(name, "t_small")) { if (value < 0 || value > 32) return SSLAPB_E_BAD_ARG; h->t_small = (int)value; return 0; }
     if (!strcmp(name, "watchdog_ms")) { if (value <= 0) return SSLAPB_E_BAD_ARG; h->watchdog_ms = value; return 0; }
     if (!strcmp(name, "t_shard")) { if (value < 0 || value > 0x7fffffff) return SSLAPB_E_BAD_ARG; h->t_shard = (int)value; return 0; }
@@ -466,14 +459,7 @@ static int reserve_auction_state(sslapb_handle *h, SslapbAuctionParams &P)
     P.bidkey = h->bidkey.as<unsigned long long>(); P.winpos = h->winpos.as<int>();
     P.hole_count = h->hole_count.as<int>(); P.chosen = h->chosen.as<double>(); P.ctrl = h->ctrl.as<SslapbCtrl>();
     P.t_small = h->t_small;
-    // opt-in: launch in clusters, a few SMs stay empty (not combined with the long-row instance).  Only with the default
-    // t_small = 32: with t_small < 32 AND grid rounds in front of the cluster rounds of a phase the randomized soak
-    // (tools/gpu_soak.py cluster) found rare wrong trajectories — an open issue, DESIGN.md 4.1b — so that combination is off.
-    static const bool cluster_any_t_small = getenv("SSLAPB_CLUSTER_ANY_TSMALL") != nullptr;   // soak runs only (tools/gpu_soak.py)
-    const bool use_cluster = h->cluster > 1 && h->t_cluster > 0 && (h->t_small == 32 || cluster_any_t_small) &&
-                             !(h->maxdeg > sslapb_coop_row_entries());
-    P.cluster = use_cluster ? h->cluster : 1;
-    P.t_cluster = use_cluster ? h->t_cluster : 0;
+    P.cluster = 1; P.t_cluster = 0;                            // (unused fields)
     P.watchdog_ns = (unsigned long long)h->watchdog_ms * 1000000ull;
     P.nranks = 1; P.rank = 0; P.t_shard = 0x7fffffff; P.rowsplit = nullptr; P.xtab = nullptr; P.xcap = 0; P.xround_base = 0;
     return SSLAPB_OK;
@@ -514,7 +500,6 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
         CK(sslapb_launch_row_split(P.rowptr, N, h->n_ranks, h->rowsplit.as<int>(), h->stream));
         P.nranks = h->n_ranks; P.rank = h->rank; P.t_shard = h->t_shard; P.rowsplit = h->rowsplit.as<int>();
         P.xtab = h->xtab.as<unsigned long long>(); P.xcap = h->xcap; P.xround_base = h->xround;
-        P.cluster = 1; P.t_cluster = 0;
     }
     SslapbCtrl c;
     memset(&c, 0, sizeof c);
@@ -525,8 +510,8 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
     c.pmax_key = 0x8000000000000000ull;
     CK(cudaMemcpyAsync(P.ctrl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
     if (warm) CK(sslapb_launch_price_bounds(&P, h->stream));   // pruning bounds of the first phase from the caller's prices
-    int grid = P.cluster > 1 ? h->cluster_grid : h->grid;
-    if (h->max_ctas > 0 && h->max_ctas < grid) { grid = h->max_ctas; if (P.cluster > 1) { P.cluster = 1; P.t_cluster = 0; } }
+    int grid = h->grid;
+    if (h->max_ctas > 0 && h->max_ctas < grid) grid = h->max_ctas;
     CK(cudaEventRecord(h->ev[3], h->stream));
     CK(sslapb_launch_auction_init(&P, grid, warm ? 1 : 0, h->stream));
     if (sharded && h->gate) {                                  // in-process ranks: nobody launches before everybody is ready
@@ -536,7 +521,7 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
             return fail(h, SSLAPB_E_ABORTED, "a rank of this process did not reach the launch of the row-sharded solve");
         }
     }
-    CK(sslapb_launch_auction(&P, grid, P.cluster, long_rows, h->coop, h->stream));
+    CK(sslapb_launch_auction(&P, grid, long_rows, h->coop, h->stream));
     CK(cudaEventRecord(h->ev[4], h->stream));
     int rs[SSLAPB_MAX_RANKS + 1] = {};
     if (sharded) CK(cudaMemcpyAsync(rs, h->rowsplit.p, sizeof rs, cudaMemcpyDeviceToHost, h->stream));
@@ -561,11 +546,6 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
         if (sharded)
             msg += " [rank " + std::to_string(h->rank) + "/" + std::to_string(h->n_ranks) + " nu=" + std::to_string(c.nu) + " its=" +
                    std::to_string(c.its) + " sharded rounds=" + std::to_string(c.rounds_sharded) + " grid=" + std::to_string(grid) + "]";
-        if (P.cluster > 1) {                                   // where the CTAs of cluster 0 were (barrier count per CTA)
-            msg += " [nu=" + std::to_string(c.nu) + " its=" + std::to_string(c.its) + " cluster barriers:";
-            for (int k = 0; k < P.cluster && k < 16; ++k) msg += " " + std::to_string(c.dbg[k]);
-            msg += "]";
-        }
         return fail(h, SSLAPB_E_ABORTED, msg);
     }
     double obj = 0.0;                                          // get_obj, auction_.pyx:489-523 (row order, double)
@@ -586,7 +566,7 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
         cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); meta->h2d_ms = ms;
         meta->n_rows = h->N; meta->n_cols = h->M; meta->nnz = h->nnz;
         meta->rounds_grid = c.rounds_grid; meta->rounds_warp = c.rounds_warp; meta->rounds_solo = c.rounds_solo;
-        meta->rounds_cluster = (int32_t)c.rounds_cluster;
+        meta->rounds_cluster = 0;                              // (the cluster regime was removed in round 2)
         for (int k = 0; k < 8; ++k) meta->prof_ms[k] = (float)((double)c.prof[k] * 1e-6);
         meta->stop_reason = c.done;
         meta->prune_second_pass = c.prune_second_pass;

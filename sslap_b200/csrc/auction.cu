@@ -13,16 +13,15 @@
 // Regimes, chosen by the frontier size nu (monotone non-increasing inside an eps-phase):
 //   grid      (nu > t_small = 32): all CTAs; warp per bidder; 64-bit atomicMax of the order-preserving bid per object
 //                                  (+ an atomicMin of the list position only in rounds where an equal bid was seen);
-//                                  3 grid barriers (spread_round<false>).
-//   cluster   (opt-in, t_small < nu <= t_cluster): the same round run by the 8 CTAs of cluster 0 with hardware cluster
-//                                  barriers (spread_round<true>; instance of auction_cluster.cu).
+//                                  3 grid barriers (spread_round).
 //   17..32    CTA 0 only; list positions strided over its 16 warps, warp 0 merges through shuffles (warp_resolve).
 //   3..16     CTA 0 only; warp a owns position a; ONE named barrier per round, outcome derived redundantly in registers
 //             (multi_rounds; the instance of auction_long.cu keeps a two-barrier form with a whole-CTA sweep of very
 //             long rows).
 //   2         warps 0 and 1 of CTA 0 (duo rounds inside multi_rounds).
 //   1         warp 0 of CTA 0, no barrier at all (chain_rounds; coop_chain_rounds when the row is long).
-// This file is compiled three times (plain, SSLAPB_LONG_ROWS, SSLAPB_CLUSTER_REGIME): see the two wrapper units.
+// This file is compiled three times (plain, SSLAPB_LONG_ROWS, SSLAPB_SHARDED): see the two wrapper units.  (Round 1's
+// opt-in cluster regime — mid-sized frontiers on one 8-CTA cluster — was removed in round 2: DESIGN.md 4.1b.)
 #include "auction.cuh"
 
 #define SSLAPB_THREADS 512       // persistent kernel: one CTA of 16 warps per SM (128 registers per thread)
@@ -170,11 +169,22 @@ __device__ __forceinline__ bool sweep_single(const SslapbAuctionParams &P, const
     const unsigned long long bk = bi >= 0 ? sslapb_key_of(lt.b) : 0ull;
     const unsigned bh = (unsigned)(bk >> 32), bl = (unsigned)bk;
     const unsigned khi = __reduce_max_sync(SSLAPB_FULL, bh);
-    const unsigned klo = __reduce_max_sync(SSLAPB_FULL, bh == khi ? bl : 0u);
-    const bool top = (bh == khi) & (bl == klo);
-    const int widx = __reduce_max_sync(SSLAPB_FULL, top ? bi : -1);
-    const bool iswin = top & (bi == widx) & (bi >= 0);
-    const unsigned own = __ballot_sync(SSLAPB_FULL, iswin);
+    // Almost always ONE lane holds the maximal high word (two candidates closer than 2^-20 relative, or exact ties, are
+    // the exception): then that lane is the winner and the low-word and row-index reductions — two dependent REDUX on
+    // the path to the next bidder's row request — are not needed.
+    const unsigned hm = __ballot_sync(SSLAPB_FULL, (bh == khi) & (bi >= 0));
+    bool iswin;
+    unsigned own;
+    if (__popc(hm) <= 1) {
+        own = hm;
+        iswin = (hm >> lane) & 1u;
+    } else {
+        const unsigned klo = __reduce_max_sync(SSLAPB_FULL, bh == khi ? bl : 0u);
+        const bool top = (bh == khi) & (bl == klo);
+        const int widx = __reduce_max_sync(SSLAPB_FULL, top ? bi : -1);
+        iswin = top & (bi == widx) & (bi >= 0);
+        own = __ballot_sync(SSLAPB_FULL, iswin);
+    }
     if (own == 0u) return false;
     const int src = __ffs(own) - 1;
     const unsigned long long wo = __shfl_sync(SSLAPB_FULL, qo, src);
@@ -961,25 +971,8 @@ __device__ __forceinline__ bool cross_barrier(const SslapbAuctionParams &P, Ssla
 }
 #endif
 
-// One Jacobi round with the bidders spread over several CTAs (auction_.pyx:337-430) — by the whole grid (grid barriers) or,
-// for mid-sized frontiers, by the CTAs of cluster 0 alone (hardware cluster barriers, ~0.25 us instead of ~1.5 us each;
-// the other CTAs wait at one grid barrier for the cluster to hand the phase over).
-__shared__ unsigned ss_cbar;                                   // cluster barriers this CTA has arrived at (zeroed by the kernel)
+// One Jacobi round with the bidders spread over all CTAs of the grid (auction_.pyx:337-430).
 struct SslapbScope { int blk, nblk, gwarp, nwarps; bool lead; };   // CTA rank / count, warp rank / count, the one reporting thread
-template <bool CLUSTER>
-__device__ __forceinline__ bool round_barrier(SslapbCtrl *C, unsigned nblk, unsigned &epoch, unsigned long long watchdog_ns)
-{
-    if (CLUSTER) {
-        // block barrier first (every warp converged, CTA-local hazards closed), then the hardware cluster barrier in its
-        // non-.aligned form: an opaque asm gives the compiler no reason to reconverge a warp in front of it
-        __syncthreads();
-        if (threadIdx.x == 0) *(volatile unsigned *)&C->dbg[blockIdx.x & 15] = ++ss_cbar;   // progress marker (watchdog report)
-        asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
-        return true;
-    }
-    return grid_barrier(C, nblk, epoch, watchdog_ns);
-}
-template <bool CLUSTER>
 __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, SslapbCtrl *C, const SslapbScope S, int nu, float eps_f,
                                              long long its, long long max_iter, double pmin, double spread, unsigned &bar_epoch,
                                              unsigned &xround)
@@ -999,7 +992,7 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
     // Row-sharded round (several GPUs, large frontier): this rank sweeps only the bidders of its own row range and stores
     // each bid into every rank's exchange buffer; after the exchange barrier every rank holds all nu bids and performs the
     // merge, the assignment and the compaction identically (the whole state is replicated, the trajectory is unchanged).
-    const bool sharded = !CLUSTER && P.nranks > 1 && nu > P.t_shard;
+    const bool sharded = P.nranks > 1 && nu > P.t_shard;
     int row_lo = 0, row_hi = 0x7fffffff;
     unsigned xk = 0;
     long long xoff = 0;
@@ -1072,7 +1065,7 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
         }
     }
 #endif
-    if (!round_barrier<CLUSTER>(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return false;
+    if (!grid_barrier(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return false;
     if (S.lead) {
         tp2 = sslapb_globaltimer();
         // in-situ full-frontier bidding step (every person bids: first round of an eps-phase), up to the barrier that
@@ -1089,7 +1082,7 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
             const int j = bidj[a];
             if (P.bidkey[j] == sslapb_ord64(bidv[a])) atomicMin(P.winpos + j, a);
         }
-        if (!round_barrier<CLUSTER>(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return false;
+        if (!grid_barrier(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return false;
     }
     // (2) assignment (:394-427), by the winner's own list position
     int myholes = 0;
@@ -1118,7 +1111,7 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
     __syncthreads();
     if (tid == 0) P.hole_count[S.blk] = s_red;
     if (S.lead) tp3 = sslapb_globaltimer();
-    if (!round_barrier<CLUSTER>(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return false;
+    if (!grid_barrier(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return false;
     if (S.lead) tp4 = sslapb_globaltimer();
     // (3) push_all_left (:137-162): k-th hole left of new_nu <- k-th live entry right of it
     if (warp == 0) {                                   // per-CTA hole counts -> total, my prefix, prefix of the split chunk
@@ -1171,15 +1164,15 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
         C->nu = new_nu;
         C->its = its + 1;
         C->tie_flag = 0;
-        if (CLUSTER) C->rounds_cluster += 1; else C->rounds_grid += 1;
+        C->rounds_grid += 1;
         if (its + 1 >= max_iter) C->done = 3;
         tp5 = sslapb_globaltimer();
 #ifdef SSLAPB_SHARDED
         if (sharded) { C->rounds_sharded += 1; C->sharded_ns += tp5 - tp0; }
 #endif
     }
-    if (!round_barrier<CLUSTER>(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return false;
-    if (S.lead && !CLUSTER) {
+    if (!grid_barrier(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return false;
+    if (S.lead) {
         C->prof[0] += tp1 - tp0; C->prof[1] += tp3 - tp2; C->prof[2] += tp5 - tp4;
         C->prof[7] += (tp2 - tp1) + (tp4 - tp3) + (sslapb_globaltimer() - tp5);
     }
@@ -1191,9 +1184,6 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
 
 #ifdef SSLAPB_LONG_ROWS
 #define sslapb_auction_kernel sslapb_auction_kernel_long   // second instance of the kernel, see auction_long.cu
-#endif
-#ifdef SSLAPB_CLUSTER_REGIME
-#define sslapb_auction_kernel sslapb_auction_kernel_cluster   // third instance, see auction_cluster.cu
 #endif
 #ifdef SSLAPB_SHARDED
 #define sslapb_auction_kernel sslapb_auction_kernel_sharded   // row-sharded multi-GPU instance, see auction_sharded.cu
@@ -1213,9 +1203,6 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
     unsigned xround = P.xround_base;                           // row-sharded rounds of this communicator so far (all CTAs agree)
 
     if (gtid == 0) C->t_begin = sslapb_globaltimer();
-#ifdef SSLAPB_CLUSTER_REGIME
-    if (tid == 0) ss_cbar = 0;
-#endif
 
     for (;;) {
         // ---- loop top: every CTA arrives here right after a grid barrier; the control block is stable.  ONE thread per
@@ -1246,36 +1233,10 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
         __syncthreads();                                       // s_top is rewritten only after every thread has read it
         if (done) break;
 
-#ifdef SSLAPB_CLUSTER_REGIME
-        if (nu > P.t_small && nu > P.t_cluster) {
-#else
         if (nu > P.t_small) {
-#endif
             // ================================ grid regime: one round ================================
             const SslapbScope S = {(int)blockIdx.x, (int)nblk, gwarp, nwarps, gtid == 0};
-            if (!spread_round<false>(P, C, S, nu, eps_f, its, max_iter, pmin, spread, bar_epoch, xround)) return;
-#ifdef SSLAPB_CLUSTER_REGIME
-        } else if (nu > P.t_small) {
-            // ================================ cluster regime: cluster 0 runs rounds until nu <= t_small ================================
-            if ((int)blockIdx.x < P.cluster) {
-                unsigned long long tc0 = 0;
-                if (gtid == 0) tc0 = sslapb_globaltimer();
-                const SslapbScope S = {(int)blockIdx.x, P.cluster, gwarp, P.cluster * wpc, gtid == 0};
-                int cnu = nu, cdone = 0;
-                long long cits = its;
-                while (!cdone && cnu > P.t_small) {
-                    spread_round<true>(P, C, S, cnu, eps_f, cits, max_iter, pmin, spread, bar_epoch, xround);
-                    if (tid == 0) { s_top.nu = *(volatile int *)&C->nu; s_top.done = *(volatile int *)&C->done; s_top.its = *(volatile long long *)&C->its; }
-                    __syncthreads();
-                    cnu = __shfl_sync(SSLAPB_FULL, s_top.nu, 0);
-                    cdone = __shfl_sync(SSLAPB_FULL, s_top.done, 0);
-                    cits = s_top.its;
-                    __syncthreads();
-                }
-                if (gtid == 0) C->prof[6] += sslapb_globaltimer() - tc0;
-            }
-            GB();
-#endif
+            if (!spread_round(P, C, S, nu, eps_f, its, max_iter, pmin, spread, bar_epoch, xround)) return;
         } else {
             // ================================ warp-list regimes: CTA 0 finishes the phase ================================
             if (blockIdx.x == 0) small_regime(P, C, nu, eps_f, its, max_iter, pmin, spread);
@@ -1371,35 +1332,32 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
     }
 }
 
-// Cooperative launch of this translation unit's kernel instance, in thread-block clusters of `cluster` CTAs when > 1.
+// Cooperative launch of this translation unit's kernel instance.
 // coop = 0: an ordinary launch.  The driver runs one cooperative kernel at a time, so several persistent kernels that must
 // make progress TOGETHER on one GPU (the virtual-rank test of the row-sharded solve: K kernels of sms/K CTAs each, one CTA
 // per SM by construction) are launched without the cooperative attribute; co-residency then rests on grid <= free SMs, and
 // the barrier watchdog turns a violation into an error instead of a hang.
-static cudaError_t launch_persistent(const SslapbAuctionParams *P, int grid, int cluster, cudaStream_t stream, int coop = 1)
+static cudaError_t launch_persistent(const SslapbAuctionParams *P, int grid, cudaStream_t stream, int coop = 1)
 {
     void *args[] = {(void *)P};
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(SSLAPB_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
-    cudaLaunchAttribute at[2];
+    cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
-    at[1].id = cudaLaunchAttributeClusterDimension;
-    at[1].val.clusterDim.x = cluster; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = cluster > 1 ? 2 : 1;
-    if (!coop) { cfg.attrs = nullptr; cfg.numAttrs = 0; }
+    cfg.attrs = at; cfg.numAttrs = coop ? 1 : 0;
     return cudaLaunchKernelExC(&cfg, (const void *)sslapb_auction_kernel, args);
 }
 #if defined(SSLAPB_LONG_ROWS)
 // (the state is initialised by sslapb_launch_auction, auction.cu)
 extern "C" cudaError_t sslapb_launch_auction_long(const SslapbAuctionParams *P, int grid, cudaStream_t stream)
 {
-    return launch_persistent(P, grid, 1, stream);
+    return launch_persistent(P, grid, stream);
 }
 extern "C" int sslapb_coop_row_entries() { return 4 * SSLAPB_COOP_CHUNKS - 3; }
 #elif defined(SSLAPB_SHARDED)
 extern "C" cudaError_t sslapb_launch_auction_sharded(const SslapbAuctionParams *P, int grid, int coop, cudaStream_t stream)
 {
-    return launch_persistent(P, grid, 1, stream, coop);
+    return launch_persistent(P, grid, stream, coop);
 }
 // nnz-balanced contiguous row split (the device-side counterpart of cumulative_idxs' row partition, auction_.pyx:33-48):
 // boundary r = first row whose CSR offset reaches r * nnz / parts (binary search over rowptr, one thread per boundary).
@@ -1420,37 +1378,6 @@ extern "C" cudaError_t sslapb_launch_row_split(const long long *rowptr, int N, i
 {
     sslapb_row_split_kernel<<<1, 32, 0, stream>>>(rowptr, N, parts, split);
     return cudaGetLastError();
-}
-#elif defined(SSLAPB_CLUSTER_REGIME)
-extern "C" cudaError_t sslapb_launch_auction_cluster(const SslapbAuctionParams *P, int grid, int cluster, cudaStream_t stream)
-{
-    return launch_persistent(P, grid, cluster, stream);
-}
-// Clusters of SSLAPB_CLUSTER CTAs, one CTA per SM: how many the device keeps co-resident (the grid is a multiple of the
-// cluster size: a B200 fits 17 clusters of 8 = 136 of its 148 SMs).  cluster = 1 when the device cannot do it.
-#define SSLAPB_CLUSTER 8
-extern "C" cudaError_t sslapb_auction_cluster_grid(int device, int *grid, int *cluster)
-{
-    int sms = 0;
-    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (e != cudaSuccess) return e;
-    *grid = sms;
-    *cluster = 1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(sms / SSLAPB_CLUSTER * SSLAPB_CLUSTER); cfg.blockDim = dim3(SSLAPB_THREADS);
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
-    at[1].id = cudaLaunchAttributeClusterDimension;
-    at[1].val.clusterDim.x = SSLAPB_CLUSTER; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 2;
-    int ncl = 0;
-    if (cudaOccupancyMaxActiveClusters(&ncl, (const void *)sslapb_auction_kernel, &cfg) == cudaSuccess && ncl >= 2) {
-        const int g = min(ncl * SSLAPB_CLUSTER, sms / SSLAPB_CLUSTER * SSLAPB_CLUSTER);
-        if (g * 10 >= sms * 8) { *grid = g; *cluster = SSLAPB_CLUSTER; }     // not worth losing more than a fifth of the SMs
-    } else {
-        cudaGetLastError();
-    }
-    return cudaSuccess;
 }
 #else
 // ----------------------------------------------------------------------------------------------------------------------
@@ -1522,22 +1449,19 @@ __global__ void sslapb_auction_init_kernel(SslapbAuctionParams P, int warm)
 }
 
 extern "C" cudaError_t sslapb_launch_auction_long(const SslapbAuctionParams *P, int grid, cudaStream_t stream);
-extern "C" cudaError_t sslapb_launch_auction_cluster(const SslapbAuctionParams *P, int grid, int cluster, cudaStream_t stream);
 // Three instances of the persistent kernel: this one (lean), auction_long.cu (the longest row exceeds
-// sslapb_coop_row_entries() entries) and auction_cluster.cu (opt-in cluster regime, cluster > 1).
+// sslapb_coop_row_entries() entries) and auction_sharded.cu (row-sharded multi-GPU solve, nranks > 1).
 extern "C" cudaError_t sslapb_launch_auction_sharded(const SslapbAuctionParams *P, int grid, int coop, cudaStream_t stream);
 extern "C" cudaError_t sslapb_launch_auction_init(const SslapbAuctionParams *P, int grid, int warm, cudaStream_t stream)
 {
     sslapb_auction_init_kernel<<<grid, 1024, 0, stream>>>(*P, warm);
     return cudaGetLastError();
 }
-extern "C" cudaError_t sslapb_launch_auction(const SslapbAuctionParams *P, int grid, int cluster, int long_rows, int coop,
-                                             cudaStream_t stream)
+extern "C" cudaError_t sslapb_launch_auction(const SslapbAuctionParams *P, int grid, int long_rows, int coop, cudaStream_t stream)
 {
     if (long_rows) return sslapb_launch_auction_long(P, grid, stream);
     if (P->nranks > 1) return sslapb_launch_auction_sharded(P, grid, coop, stream);
-    if (cluster > 1) return sslapb_launch_auction_cluster(P, grid, cluster, stream);
-    return launch_persistent(P, grid, 1, stream);
+    return launch_persistent(P, grid, stream);
 }
 
 extern "C" cudaError_t sslapb_auction_grid_size(int device, int *grid)

@@ -5,7 +5,7 @@
 // Control block in device memory: the only cross-CTA communication channel of the persistent kernel.
 struct SslapbCtrl {
     // ---- line 0: the words the waiting CTAs poll (up to 147 CTAs, ~100 loads per microsecond on this one L2 line while
-    // CTA 0 or cluster 0 runs a phase alone) — nothing the working CTAs touch per round may share it
+    // CTA 0 runs a phase alone) — nothing the working CTAs touch per round may share it
     unsigned bar_count;       // grid barrier: arrivals
     unsigned bar_gen;         // grid barrier: generation
     int abort_flag;           // set by the watchdog (a barrier waited longer than watchdog_ns) or an internal assert
@@ -23,16 +23,16 @@ struct SslapbCtrl {
     int tie_flag;             // some atomicMax saw an equal bid this round -> run the position tie-break pass
     int ece_final;            // meta['eCE'] (:297); -1 until known
     long long rounds_grid, rounds_warp, rounds_solo;   // instrumentation: rounds executed per regime
-    long long rounds_cluster;                          // ... and by cluster 0 alone (mid-sized frontiers)
+    long long rounds_cluster;                          // (unused: round 1's cluster regime was removed)
     unsigned long long pmin_key[2];                    // order-preserving image of a LOWER bound of every price (slot = phase & 1);
                                                        // prices never decrease, so a phase-start minimum stays valid all phase
     unsigned long long pmax_key;                       // running maximum of the prices (atomicMax by every winner): heuristic only
     long long prune_second_pass;                       // instrumentation: rows that needed the second (exactness) gather pass
     unsigned long long t_begin, t_end;                 // %globaltimer at kernel start / end
-    unsigned dbg[16];                                  // cluster regime: last barrier each CTA of cluster 0 arrived at
+    unsigned dbg[16];                                  // (unused)
                                                        // ((round << 3) | barrier index), reported when the watchdog fires
     unsigned long long prof[8];                        // ns spent (CTA 0 view): 0 grid bid, 1 grid tie+assign, 2 grid compaction,
-                                                       // 3 warp regime, 4 solo regime, 5 eCE/phase change, 6 cluster regime, 7 barriers of the grid regime
+                                                       // 3 warp regime, 4 solo regime, 5 eCE/phase change, 6 (unused), 7 barriers of the grid regime
     long long rounds_sharded;                          // row-sharded solve: rounds whose bidding was split over the ranks
     unsigned long long xchg_ns;                        // ... ns CTA 0 spent in their cross-GPU exchange barrier (signal + wait)
     unsigned long long sharded_ns;                     // ... ns of those rounds in total (CTA 0 view)
@@ -72,8 +72,7 @@ struct SslapbAuctionParams {
     double *chosen;           // per person: sum of (folded) values of entries equal to its object (get_obj, :504-521)
     SslapbCtrl *ctrl;
     int t_small;              // nu <= t_small (<= 32) -> CTA 0 runs the round alone (warp-list regime)
-    int t_cluster;            // t_small < nu <= t_cluster -> the CTAs of cluster 0 run the rounds (0: regime off)
-    int cluster;              // CTAs per cluster of the launch (1: no clusters)
+    int t_cluster, cluster;   // (unused: round 1's cluster regime was removed; kept so that the layout is unchanged)
     unsigned long long watchdog_ns;
     // ---- row-sharded solve over several GPUs (instance of auction_sharded.cu; nranks == 1: off).  Persons are split into
     // nnz-balanced contiguous row ranges; every rank holds the whole state and CSR, but in rounds with nu > t_shard it sweeps

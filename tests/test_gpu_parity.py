@@ -404,37 +404,12 @@ def test_very_long_rows_use_the_cooperative_kernel_instance(gpu, oracle_mod):
             assert np.array_equal(prices_of(nat, h, mat.shape[1]), want["prices"]), name
 
 
-def test_cluster_regime_opt_in_bit_exact(gpu, oracle_mod):
-    """Opt-in regime ("t_cluster" > 0): the kernel is launched in thread-block clusters and cluster 0 alone runs the
-    rounds of mid-sized frontiers with hardware cluster barriers.  Same trajectory: sol, meta and prices bit-exact."""
-    sslap_b200, nat, h = gpu
-    cases = [(1000, 0.01, "int", 0), (4000, 0.01, "float", 1), (10000, 0.01, "float", 0), (300, 0.3, "float", 5)]
-    h.set_option("watchdog_ms", 20000)
-    try:
-        for (n, d, mode, seed) in cases:
-            loc, val = make_problem(n, d, mode, seed=seed)
-            want = oracle_mod.auction_solve(loc=loc, val=val, problem="max", return_prices=True, max_iter=60000)
-            for (t_small, t_cluster) in ((32, 512), (32, 64), (32, 100000)):     # (the regime is only enabled with t_small = 32)
-                h.set_option("t_small", t_small)
-                h.set_option("t_cluster", t_cluster)
-                got = sslap_b200.auction_solve(loc=loc, val=val, size=(n, n), problem="max", cardinality_check=False,
-                                               max_iter=60000, _raw_meta=True)
-                assert got["raw"].rounds_cluster > 0
-                assert np.array_equal(got["sol"], want["sol"]), (n, t_small, t_cluster)
-                assert_meta_equal(got["meta"], want["meta"])
-                assert np.array_equal(prices_of(nat, h, n), want["prices"])
-    finally:
-        h.set_option("t_small", 32)
-        h.set_option("t_cluster", 0)
-        h.set_option("watchdog_ms", 120000)
-
-
 def test_two_handles_in_two_threads_and_option_validation(gpu, oracle_mod):
     """One handle = one stream + its own scratch; distinct handles may be driven from different threads (the persistent
     cooperative kernels of the two solves simply take turns on the device).  Options reject bad values."""
     import threading
     sslap_b200, nat, h = gpu
-    for name, value in (("t_small", 33), ("t_small", -1), ("t_cluster", -5), ("watchdog_ms", 0), ("no_such_option", 1)):
+    for name, value in (("t_small", 33), ("t_small", -1), ("t_cluster", 64), ("t_shard", -5), ("watchdog_ms", 0), ("no_such_option", 1)):
         with pytest.raises(ValueError):
             h.set_option(name, value)
     problems = [make_problem(n, d, "float", seed=s) for (n, d, s) in ((1500, 0.01, 1), (900, 0.03, 2), (2500, 0.004, 3))]
