@@ -198,8 +198,8 @@ extern "C" void sslapb_destroy(sslapb_handle *h)
                      &h->hole_count, &h->chosen, &h->ctrl, &h->bidders, &h->flush, &h->sweep_plan, &h->pair_u, &h->pair_v, &h->dist,
                      &h->visited, &h->cursor, &h->pred, &h->hkflags, &h->hkq};
     for (DevBuf *b : all) b->release();
-    for (int r = 0; r < 8; ++r) if (h->peer_ipc[r] && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
-    h->xbuf.release(); h->xtab.release(); h->rowsplit.release(); h->warm.release();
+    sslapb_comm_destroy(h);                                    // peer mappings, exchange buffer, the process-local launch gate
+    h->rowsplit.release(); h->warm.release();
     for (auto &ev : h->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -805,7 +805,9 @@ extern "C" int sslapb_comm_connect(sslapb_handle *h, const void *all_exports)
         std::lock_guard<std::mutex> g(g_gates_mu);
         h->gate_key = E[0].base;
         auto &slot = g_gates[h->gate_key];
-        if (!slot) { slot = std::make_shared<LocalGate>(); slot->n = h->n_ranks; }
+        // a gate left behind by an earlier communicator whose rank 0 buffer had the same address is never reused:
+        // only the map itself holding it (use_count 1), or a different size, means it is stale
+        if (!slot || slot.use_count() == 1 || slot->n != h->n_ranks) { slot = std::make_shared<LocalGate>(); slot->n = h->n_ranks; }
         h->gate = slot;
     }
     CK(h->xtab.reserve(sizeof tab));

@@ -6,6 +6,11 @@ import sys
 import numpy as np
 import pytest
 
+# The virtual-rank test runs up to 8 persistent kernels side by side on ONE device, each on its own stream; with the default
+# of 8 hardware work queues two of those streams can share a queue, and the second kernel then waits for the first to
+# finish — which it never does.  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -216,7 +216,7 @@ def test_row_sharded_solve_with_virtual_ranks_on_one_gpu(gpu, oracle_mod, k_rank
                 t.start()
             for t in threads:
                 t.join()
-            assert not errors, errors
+            assert not errors, "\n".join(f"rank {r}: {e}" for r, e in errors)
             indptr = np.searchsorted(loc[:, 0], np.arange(n + 1))
             split = parallel.balanced_row_split(indptr, k_ranks)
             for r in range(k_ranks):
