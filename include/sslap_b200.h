@@ -26,7 +26,7 @@ extern "C" {
 
 typedef struct sslapb_handle sslapb_handle;
 
-#define SSLAPB_ABI_VERSION 2      /* bumped whenever struct sslapb_meta or a prototype changes */
+#define SSLAPB_ABI_VERSION 3      /* bumped whenever struct sslapb_meta or a prototype changes */
 
 enum {
     SSLAPB_OK = 0,
@@ -81,6 +81,9 @@ typedef struct sslapb_meta {
     int32_t sweep_insitu_n;  /* number of such rounds */
     int32_t warm_start;      /* 1 when the solve started from caller-supplied prices (sslapb_set_prices) */
     int32_t strict;          /* 1 when the strict-optimality stop rule was on (option "strict") */
+    /* ---- ABI version 3: hot lists (the 32 largest entries of every row decide a bid when that is provably exact) */
+    int64_t hot_grid_bids, hot_grid_fallbacks;   /* grid-regime bids decided by the hot list / handed on to the full-row sweep */
+    int64_t hot_tail_rounds, hot_tail_fallbacks; /* few-bidder + chain rounds run in hot form / their bids handed on to the full row */
 } sslapb_meta;
 
 int  sslapb_create(int device, sslapb_handle **out);
@@ -97,6 +100,7 @@ int    sslapb_abi_version(void);
    "hk_host_loop" (1: Hopcroft-Karp phases driven from the host with one read-back per BFS level, as in round 1, instead of the
    device-resident loop; A/B runs; default 0),
    "batch_v1" (1: round 1's batch kernel — a whole warp sweeps one bidder at a time — instead of the sub-warp kernel; A/B runs),
+   "hot" (0: never decide bids from the hot lists — A/B runs; default 1),
    "coop" (row-sharded solves only; 0: launch the persistent kernel without the cooperative attribute so that several of them
    can run side by side on ONE GPU — the driver runs one cooperative kernel at a time; only for the virtual-rank test, default 1),
    "strict" (1: strict-optimality stop rule — eps-CS is tested with eps = 1/(N+1) and zero tolerance and the eps schedule runs

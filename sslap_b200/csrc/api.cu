@@ -25,6 +25,7 @@ cudaError_t sslapb_launch_coo_ingest(const void *, const void *, int, long long,
 cudaError_t sslapb_launch_coo_sort(const void *, const void *, int, long long, const double *, long long, int, unsigned *,
                                    unsigned *, unsigned *, unsigned *, long long *, int *, int *, double *, int, cudaStream_t);
 cudaError_t sslapb_launch_rowmax(const long long *, const double *, long long, double *, int *, int, cudaStream_t);
+cudaError_t sslapb_launch_hot_build(const long long *, const int *, const double *, int, SslapbHotEnt *, double *, int, cudaStream_t);
 cudaError_t sslapb_launch_index_max(const void *, const void *, int, long long, long long, long long *, int, cudaStream_t);
 cudaError_t sslapb_launch_dense_count(const double *, int, int, long long *, SslapbBuildFlags *, int, cudaStream_t);
 cudaError_t sslapb_launch_dense_fill(const double *, int, int, int, const long long *, int *, double *,
@@ -117,6 +118,9 @@ struct sslapb_handle {
     int max_ctas = 0;              // upper bound of the persistent kernel's grid (0: one CTA per SM)
     int strict = 0;                // strict-optimality stop rule (see the header)
     int coop = 1;                  // 0: launch the row-sharded persistent kernel without the cooperative attribute (virtual ranks)
+    int hot = 1;                   // hot lists (hot.cu): 0 = off (A/B runs)
+    size_t l2_persist_max = 0;     // cudaDevAttrMaxPersistingL2CacheSize
+    int l2_window_max = 0;         // cudaDevAttrMaxAccessPolicyWindowSize
     // warm start: prices for the next solve (sslapb_set_prices)
     DevBuf warm;
     int warm_cols = 0;
@@ -136,6 +140,7 @@ struct sslapb_handle {
     long long nnz = 0;
     bool has_vals = false;
     DevBuf stage_idx, stage_val, stage_mat, cols, vals, rowptr, rowmax, flags;
+    DevBuf hotbuf;                 // rest[N] | hthr[N] | hot lists N x 512 B (one allocation: one L2 access-policy window covers it)
     DevBuf sort_keys, sort_idx, sort_hist, sort_rows, sort_cols, sort_val;   // only for unsorted input
     DevBuf b_off, b_rows, b_cols, b_eps, b_meta, b_bad, b_rec;               // batched problems
     int batch_v1 = 0;              // option "batch_v1": 1 = round 1's batch kernel (whole warp per bidder), A/B runs
@@ -183,6 +188,14 @@ extern "C" int sslapb_create(int device, sslapb_handle **out)
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete h; return -(int)e; }
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     if ((e = sslapb_auction_grid_size(device, &h->grid)) != cudaSuccess) { delete h; return -(int)e; }
+    {   // L2 persistence for the hot lists of the tail rounds (run_auction sets the window per launch)
+        int pmax = 0, wmax = 0;
+        cudaDeviceGetAttribute(&pmax, cudaDevAttrMaxPersistingL2CacheSize, device);
+        cudaDeviceGetAttribute(&wmax, cudaDevAttrMaxAccessPolicyWindowSize, device);
+        h->l2_persist_max = (size_t)(pmax > 0 ? pmax : 0); h->l2_window_max = wmax > 0 ? wmax : 0;
+        if (pmax > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)pmax);
+        cudaGetLastError();
+    }
     if ((e = sslapb_hk_persistent_grid(device, &h->hk_grid)) != cudaSuccess) { delete h; return -(int)e; }
     *out = h;
     return SSLAPB_OK;
@@ -196,7 +209,7 @@ extern "C" void sslapb_destroy(sslapb_handle *h)
     DevBuf *all[] = {&h->b_rec, &h->b_off, &h->b_rows, &h->b_cols, &h->b_eps, &h->b_meta, &h->b_bad, &h->sort_keys, &h->sort_idx, &h->sort_hist, &h->sort_rows, &h->sort_cols, &h->sort_val, &h->stage_idx, &h->stage_val, &h->stage_mat, &h->cols, &h->vals, &h->rowptr, &h->rowmax, &h->flags, &h->price,
                      &h->owner, &h->p2o, &h->list, &h->mover, &h->bidj, &h->bidv, &h->bidkey, &h->winpos,
                      &h->hole_count, &h->chosen, &h->ctrl, &h->bidders, &h->flush, &h->sweep_plan, &h->pair_u, &h->pair_v, &h->dist,
-                     &h->visited, &h->cursor, &h->pred, &h->hkflags, &h->hkq};
+                     &h->visited, &h->cursor, &h->pred, &h->hkflags, &h->hkq, &h->hotbuf};
     for (DevBuf *b : all) b->release();
     sslapb_comm_destroy(h);                                    // peer mappings, exchange buffer, the process-local launch gate
     h->rowsplit.release(); h->warm.release();
@@ -222,6 +235,7 @@ extern "C" int sslapb_set_option(sslapb_handle *h, const char *name, int64_t val
     if (!strcmp(name, "strict")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->strict = (int)value; return 0; }
     if (!strcmp(name, "hk_host_loop")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->hk_host_loop = (int)value; return 0; }
     if (!strcmp(name, "batch_v1")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->batch_v1 = (int)value; return 0; }
+    if (!strcmp(name, "hot")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->hot = (int)value; return 0; }
     if (!strcmp(name, "coop")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->coop = (int)value; return 0; }
     return fail(h, SSLAPB_E_BAD_ARG, std::string("unknown option ") + name);
 }
@@ -454,6 +468,7 @@ static int reserve_auction_state(sslapb_handle *h, SslapbAuctionParams &P)
     P.N = h->N; P.M = h->M;
     P.rowptr = h->rowptr.as<long long>(); P.cols = h->cols.as<int>(); P.vals = h->vals.as<double>();
     P.rowmax = h->rowmax.as<double>();
+    P.hot = nullptr; P.hthr = nullptr; P.rest = nullptr;
     P.price = h->price.as<double>(); P.rec = h->owner.as<SslapbObjRec>(); P.p2o = h->p2o.as<int>();
     P.list = h->list.as<int>(); P.mover = h->mover.as<int>(); P.bidj = h->bidj.as<int>(); P.bidv = h->bidv.as<double>();
     P.bidkey = h->bidkey.as<unsigned long long>(); P.winpos = h->winpos.as<int>();
@@ -512,6 +527,29 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
     if (warm) CK(sslapb_launch_price_bounds(&P, h->stream));   // pruning bounds of the first phase from the caller's prices
     int grid = h->grid;
     if (h->max_ctas > 0 && h->max_ctas < grid) grid = h->max_ctas;
+    // ---- hot lists (hot.cu): the 32 largest entries of every row + the bound of the rest; not for the long-row instance
+    bool l2_window = false;
+    if (h->hot && !long_rows && N > 32) {
+        const size_t head = (((size_t)N * 16) + 511) & ~(size_t)511, total = head + (size_t)N * 512;
+        CK(h->hotbuf.reserve(total));
+        char *hb = h->hotbuf.as<char>();
+        P.rest = reinterpret_cast<double *>(hb); P.hthr = reinterpret_cast<double *>(hb) + N;
+        SslapbHotEnt *hot = reinterpret_cast<SslapbHotEnt *>(hb + head);
+        P.hot = hot;
+        CK(sslapb_launch_hot_build(P.rowptr, P.cols, P.vals, N, hot, const_cast<double *>(P.hthr), h->sms, h->stream));
+        if (h->l2_persist_max > 0 && h->l2_window_max > 0) {   // loads from the hot lists (and rest[]) stay in L2 across the phase
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof av);
+            const size_t win = total < (size_t)h->l2_window_max ? total : (size_t)h->l2_window_max;
+            av.accessPolicyWindow.base_ptr = hb;
+            av.accessPolicyWindow.num_bytes = win;
+            av.accessPolicyWindow.hitRatio = win <= h->l2_persist_max ? 1.0f : (float)((double)h->l2_persist_max / (double)win);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            l2_window = cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+            cudaGetLastError();
+        }
+    }
     CK(cudaEventRecord(h->ev[3], h->stream));
     CK(sslapb_launch_auction_init(&P, grid, warm ? 1 : 0, h->stream));
     if (sharded && h->gate) {                                  // in-process ranks: nobody launches before everybody is ready
@@ -523,6 +561,12 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
     }
     CK(sslapb_launch_auction(&P, grid, long_rows, h->coop, h->stream));
     CK(cudaEventRecord(h->ev[4], h->stream));
+    if (l2_window) {                                           // later launches on this stream: no window, persisting lines released
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof av);
+        cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();
+    }
     int rs[SSLAPB_MAX_RANKS + 1] = {};
     if (sharded) CK(cudaMemcpyAsync(rs, h->rowsplit.p, sizeof rs, cudaMemcpyDeviceToHost, h->stream));
     std::vector<double> chosen((size_t)N);
@@ -537,6 +581,7 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
     CK(cudaMemcpyAsync(chosen.data(), P.chosen, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&c, P.ctrl, sizeof c, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (l2_window) { cudaCtxResetPersistingL2Cache(); cudaGetLastError(); }
     if (sharded) {
         h->xround += (unsigned)c.rounds_sharded;
         if (c.abort_flag) h->comm_broken = true;               // the ranks may have left the solve at different rounds
@@ -577,6 +622,8 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
         meta->sweep_insitu_n = (int32_t)c.sweep_ns[1];
         meta->sweep_insitu_us = c.sweep_ns[1] ? (float)((double)c.sweep_ns[0] * 1e-3 / (double)c.sweep_ns[1]) : 0.f;
         meta->warm_start = warm ? 1 : 0; meta->strict = h->strict;
+        meta->hot_grid_bids = c.hot_grid[0]; meta->hot_grid_fallbacks = c.hot_grid[1];
+        meta->hot_tail_rounds = c.hot_tail[0]; meta->hot_tail_fallbacks = c.hot_tail[1];
         (void)assigned;
     }
     return SSLAPB_OK;
@@ -843,11 +890,11 @@ extern "C" int sslapb_bid_sweep(sslapb_handle *h, const double *prices, const in
     // bit 2 of `merge`: identity frontier through the streamed (TMA ring) sweep, sweep_tma.cu — bit-identical results,
     // measured slower than the per-row kernel on B200, kept for A/B runs
     const bool streamed = !d_bidders && nb == h->N && (merge & 4);
-    // variants of the sweep, all bit-identical (A/B runs): bit 7 = the per-row kernel (one warp per row, 32
-    // warps per SM); bit 3 = the software-pipelined per-row kernel (sweep2.cu; bits 4-5: its CTA size 768 / 1024 / 640 / 512,
-    // bit 6: untrimmed stage C); default = four rows per warp, 8 lanes per row (sweep4.cu)
-    const bool per_row = (merge & 128) != 0;
+    // variants of the sweep, all bit-identical (A/B runs): default = the per-row kernel (one warp per row, 32
+    // warps per SM — the fastest measured); bit 3 = the software-pipelined per-row kernel (sweep2.cu; bits 4-5: its CTA size
+    // 768 / 1024 / 640 / 512, bit 6: untrimmed stage C); bit 7 = four rows per warp, 8 lanes per row (sweep4.cu)
     const bool pipelined = (merge & 8) != 0;
+    const bool per_row = !pipelined && (merge & 128) == 0;
     static const int sw2_threads[4] = {768, 1024, 640, 512};
     const int threads2 = sw2_threads[(merge >> 4) & 3];
     const int lean2 = (merge & 64) ? 0 : 1;                    // bit 6: the untrimmed stage C (A/B)

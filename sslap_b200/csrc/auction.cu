@@ -210,6 +210,86 @@ __device__ __forceinline__ bool sweep_single(const SslapbAuctionParams &P, const
     return true;
 }
 
+// ---- hot-list form of the same step (hot.cu): lane t holds hot entry t of the bidder — ONE record gather per lane, no
+// per-lane tournament, a 512-byte row that stays in L2.  Returns false when the hot list cannot prove its answer (the
+// second-best value found is not above the bound of the entries outside the list) or finds no candidate: the caller then
+// sweeps the full row.  The next bidder's hot row is requested as early as in sweep_single.
+struct SslapbHotRow { int col, idx; double a, rest; };
+__device__ __forceinline__ SslapbHotRow sslapb_load_hot(const SslapbAuctionParams &P, int person, bool active)
+{
+    SslapbHotRow h;
+    h.col = -1; h.idx = -1; h.a = SSLAPB_NEG_INF; h.rest = __longlong_as_double(0x7ff0000000000000ll);
+    if (active) {
+        const int4 q = __ldg(reinterpret_cast<const int4 *>(P.hot) + (long long)person * 32 + (threadIdx.x & 31));
+        h.col = q.x; h.idx = q.y; h.a = __hiloint2double(q.w, q.z);
+        h.rest = P.rest[person];                               // any earlier value of the bound is still a valid bound
+    }
+    return h;
+}
+__device__ __forceinline__ bool sweep_hot(const SslapbAuctionParams &P, const SslapbHotRow &cur, double eps, bool want_next,
+                                          SslapbBid &B, SslapbHotRow &nxt)
+{
+    const int lane = threadIdx.x & 31;
+    SslapbRec256 q;
+    q.start = 0ull; q.owner_deg = 0xffffffffull; q.price_bits = 0ull;
+    const bool m = cur.col >= 0;
+    if (m) q = sslapb_ld_rec256(P.rec + cur.col);
+    const double v = m ? cur.a - __longlong_as_double((long long)q.price_bits) : SSLAPB_NEG_INF;
+    const bool has = v > SSLAPB_NEG_INF;
+    const unsigned long long bk = has ? sslapb_key_of(v) : 0ull;
+    const unsigned bh = (unsigned)(bk >> 32), bl = (unsigned)bk;
+    const unsigned khi = __reduce_max_sync(SSLAPB_FULL, bh);
+    const unsigned hm = __ballot_sync(SSLAPB_FULL, (bh == khi) & has);
+    bool iswin;
+    unsigned own;
+    if (__popc(hm) <= 1) {
+        own = hm;
+        iswin = (hm >> lane) & 1u;
+    } else {
+        const unsigned klo = __reduce_max_sync(SSLAPB_FULL, bh == khi ? bl : 0u);
+        const bool top = (bh == khi) & (bl == klo) & has;
+        const int widx = __reduce_max_sync(SSLAPB_FULL, top ? cur.idx : -1);   // equal values: the later row entry wins (:351)
+        iswin = top & (cur.idx == widx);
+        own = __ballot_sync(SSLAPB_FULL, iswin);
+    }
+    nxt = cur;
+    if (own == 0u) return false;
+    const int src = __ffs(own) - 1;
+    const unsigned long long wo = __shfl_sync(SSLAPB_FULL, q.owner_deg, src);
+    B.pstart = (long long)__shfl_sync(SSLAPB_FULL, q.start, src);
+    B.powner = (int)(unsigned)wo;
+    B.pdeg = (int)(wo >> 32);
+    nxt = sslapb_load_hot(P, B.powner, want_next && B.powner >= 0);
+    // ---- everything below overlaps the load above
+    const unsigned long long cand = iswin ? 0ull : bk;         // one candidate per lane: second best = best of the other lanes
+    const unsigned chh = (unsigned)(cand >> 32), chl = (unsigned)cand;
+    const unsigned shi = __reduce_max_sync(SSLAPB_FULL, chh);
+    const unsigned slo = __reduce_max_sync(SSLAPB_FULL, chh == shi ? chl : 0u);
+    const unsigned long long skey = ((unsigned long long)shi << 32) | slo;
+    const double bc = __shfl_sync(SSLAPB_FULL, cur.a, src);
+    B.j = __shfl_sync(SSLAPB_FULL, cur.col, src);
+    const double wi = skey > SSLAPB_KEY_NEG_INF ? sslapb_key2double(skey) : SSLAPB_NEG_INF;   // :344
+    B.bid = (bc - wi) + eps;                                   // :360
+    return (wi > cur.rest) || (cur.rest == SSLAPB_NEG_INF);
+}
+
+// One bidder of the few-bidder / chain regimes in hot form: decide from the hot list, otherwise sweep the full row with the
+// exact generic sweep (bound-pruned when the row is longer than one warp pass) and request the next occupant's hot row.
+// `fell` counts the bids the hot list could not decide.  Returns false for a row without any entry.
+__device__ __forceinline__ bool hot_bid(const SslapbAuctionParams &P, const SslapbHotRow &cur, int me, long long st, int dg,
+                                        double eps, const double *s_bounds, bool want_next, SslapbBid &B, SslapbHotRow &nxt,
+                                        int &fell)
+{
+    if (sweep_hot(P, cur, eps, want_next, B, nxt)) return true;
+    ++fell;
+    const bool single = (((st + dg + 3) >> 2) - (st >> 2)) <= 32;
+    B = row_bid_rec<32>(P.cols, P.vals, P.rec, st, st + dg, threadIdx.x & 31, eps, s_bounds[0],
+                        single ? SSLAPB_NEG_INF : __ldg(P.rowmax + me) - s_bounds[1]);
+    const bool ok = B.j >= 0;
+    nxt = sslapb_load_hot(P, B.powner, ok && want_next && B.powner >= 0);
+    return ok;
+}
+
 // The winner's writes (auction_.pyx:397-418) — executed by one lane.
 __device__ __forceinline__ void commit_win(const SslapbAuctionParams &P, int person, long long st, int dg, const SslapbBid &B)
 {
@@ -538,6 +618,169 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
     return nu;
 }
 
+#ifndef SSLAPB_LONG_ROWS
+// ----------------------------------------------------------------------------------------------------------------------
+// Hot-list forms of chain_rounds / multi_rounds (hot.cu), used in the eps-phases whose probing round found the hot lists
+// decisive.  Same round structure, same publications, same commits — only the sweep differs: 512 bytes and one record
+// gather per lane instead of the full row and four, and whatever the hot list cannot prove goes to the exact generic sweep.
+// ----------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int chain_rounds_hot(const SslapbAuctionParams &P, double eps, const double *s_bounds, int &li,
+                                                long long &lst, int &ldg, long long &its, long long max_iter, int &done,
+                                                long long &rounds, int &fell)
+{
+    const int lane = threadIdx.x & 31;
+    li = __shfl_sync(SSLAPB_FULL, li, 0); lst = __shfl_sync(SSLAPB_FULL, lst, 0); ldg = __shfl_sync(SSLAPB_FULL, ldg, 0);
+    int nu = 1;
+    SslapbHotRow cur = sslapb_load_hot(P, li, true);
+    while (nu == 1 && !done) {
+        SslapbBid B;
+        SslapbHotRow nxt;
+        if (!sweep_hot(P, cur, eps, its + 1 < max_iter, B, nxt)) {
+            ++fell;
+            // undecided: rows of more than one warp pass are left to the whole CTA (coop_chain_rounds), the others are
+            // swept exactly (every entry gathered) right here
+            if ((((lst + ldg + 3) >> 2) - (lst >> 2)) > 32) break;
+            B = row_bid_rec<32>(P.cols, P.vals, P.rec, lst, lst + ldg, lane, eps);
+            if (B.j < 0) { done = 4; break; }
+            nxt = sslapb_load_hot(P, B.powner, B.powner >= 0);
+        }
+        if (lane == 0) commit_win(P, li, lst, ldg, B);         // the only bidder wins (:379-385, :394-427)
+        __syncwarp();
+        ++its; ++rounds;
+        if (its >= max_iter) done = 3;
+        if (B.powner < 0) { nu = 0; li = -1; break; }          // nobody evicted: the frontier is empty
+        li = B.powner; lst = B.pstart; ldg = B.pdeg;           // the evicted owner is the next (and only) bidder
+        cur = nxt;
+    }
+    return nu;
+}
+
+__device__ __forceinline__ int multi_rounds_hot(const SslapbAuctionParams &P, double eps, const double *s_bounds, int nu,
+                                                const int *s_list, const long long *s_start, const int *s_deg,
+                                                long long &its, long long max_iter, int &done, long long &rounds, int &me,
+                                                long long &st, int &dg, int &fell)
+{
+    const int lane = threadIdx.x & 31, a = __shfl_sync(SSLAPB_FULL, (int)(threadIdx.x >> 5), 0);
+    bool active = a < nu;
+    SslapbHotRow cur = sslapb_load_hot(P, 0, false);
+    me = -1; st = 0; dg = 0;
+    if (active) {
+        me = s_list[a]; st = s_start[a]; dg = s_deg[a];
+        cur = sslapb_load_hot(P, me, true);
+    }
+    // ---- 3..16 bidders, one named barrier per round among the active warps (see multi_rounds)
+    __shared__ SslapbDuoPub s_hpub[2][SSLAPB_THREADS / 32];
+    int par = 0;
+    int bar_warps = nu;
+    while (active && nu > 2 && !done) {
+        SslapbBid B;
+        B.j = -1; B.bid = 0.0; B.powner = -1; B.pdeg = 0; B.pstart = 0;
+        SslapbHotRow nxt;
+        if (!hot_bid(P, cur, me, st, dg, eps, s_bounds, true, B, nxt, fell)) B.j = -1;
+        if (lane == 0) {
+            SslapbDuoPub pb;
+            pb.bid = B.bid; pb.pstart = B.pstart; pb.st = st; pb.j = B.j; pb.powner = B.powner; pb.pdeg = B.pdeg;
+            pb.me = me; pb.dg = dg; pb.pad = 0;
+            s_hpub[par][a] = pb;
+        }
+        asm volatile("bar.sync 2, %0;" ::"r"(bar_warps * 32) : "memory");
+        SslapbDuoPub O;
+        O.bid = 0.0; O.pstart = 0; O.st = 0; O.j = -1 - lane; O.powner = -1; O.pdeg = 0; O.me = -1; O.dg = 0; O.pad = 0;
+        if (lane < nu) O = s_hpub[par][lane];
+        par ^= 1;
+        if (__any_sync(SSLAPB_FULL, lane < nu && O.j < 0)) { done = 4; break; }   // empty row: rejected at CSR build
+        bool beaten = false;
+        for (int c = 0; c < nu; ++c) {
+            const int cj = __shfl_sync(SSLAPB_FULL, O.j, c);
+            const double cb = __shfl_sync(SSLAPB_FULL, O.bid, c);
+            beaten |= (c != lane) && (cj == O.j) && (cb > O.bid || (cb == O.bid && c < lane));
+        }
+        const bool wonb = (lane < nu) && !beaten;              // position `lane` wins its object
+        const int nme_b = wonb ? O.powner : O.me;              // next occupant of position `lane`; -1 = hole
+        const long long nst_b = wonb ? O.pstart : O.st;
+        const int ndg_b = wonb ? O.pdeg : O.dg;
+        const bool won = __shfl_sync(SSLAPB_FULL, (int)wonb, a) != 0;
+        if (wonb) {                                            // every active warp stores every winner's record (see multi_rounds)
+            SslapbBid Wb;
+            Wb.j = O.j; Wb.bid = O.bid; Wb.powner = O.powner; Wb.pdeg = O.pdeg; Wb.pstart = O.pstart;
+            commit_win(P, O.me, O.st, O.dg, Wb);
+        }
+        __syncwarp();
+        ++its; ++rounds;
+        if (its >= max_iter) done = 3;
+        const unsigned holes = __ballot_sync(SSLAPB_FULL, lane < nu && nme_b < 0);
+        const int new_nu = nu - __popc(holes);
+        int src = a;
+        if (holes) {
+            const unsigned valid = (1u << nu) - 1u, leftm = (1u << new_nu) - 1u;
+            const unsigned left_holes = holes & leftm, right_live = valid & ~holes & ~leftm;
+            if (a < new_nu && ((left_holes >> a) & 1u)) {
+                unsigned m = right_live;
+                for (int q = __popc(left_holes & ((1u << a) - 1u)); q > 0; --q) m &= m - 1u;
+                src = __ffs(m) - 1;
+            }
+        }
+        const int e_me = __shfl_sync(SSLAPB_FULL, nme_b, src);
+        const long long e_st = __shfl_sync(SSLAPB_FULL, nst_b, src);
+        const int e_dg = __shfl_sync(SSLAPB_FULL, ndg_b, src);
+        bar_warps = nu;
+        nu = new_nu;
+        active = a < nu;
+        if (!active) {                                         // my position fell off the end
+            if (nu > 2 && !done) asm volatile("bar.arrive 2, %0;" ::"r"(bar_warps * 32) : "memory");
+            me = -1;
+            break;
+        }
+        me = e_me; st = e_st; dg = e_dg;
+        if (src == a && won) cur = nxt;                        // the evicted owner: hot row already requested
+        else if (src != a) cur = sslapb_load_hot(P, me, true); // moved here by the compaction
+        // (lost: same person, same hot row, still in registers)
+    }
+    // ---- exactly two bidders: warps 0 and 1, closed-form outcome (see the duo rounds of multi_rounds)
+    if (nu == 2 && !done && a < 2) {
+        __shared__ SslapbDuoPub s_hduo[2][2];
+        int dpar = 0;
+        while (nu == 2 && !done) {
+            SslapbBid B;
+            B.j = -1; B.bid = 0.0; B.powner = -1; B.pdeg = 0; B.pstart = 0;
+            SslapbHotRow nxt;
+            if (!hot_bid(P, cur, me, st, dg, eps, s_bounds, true, B, nxt, fell)) B.j = -1;
+            if (lane == 0) {
+                SslapbDuoPub pb;
+                pb.bid = B.bid; pb.pstart = B.pstart; pb.st = st; pb.j = B.j; pb.powner = B.powner; pb.pdeg = B.pdeg;
+                pb.me = me; pb.dg = dg; pb.pad = 0;
+                s_hduo[dpar][a] = pb;
+            }
+            asm volatile("bar.sync 3, 64;" ::: "memory");
+            const SslapbDuoPub O = s_hduo[dpar][a ^ 1];
+            dpar ^= 1;
+            if (B.j < 0 || O.j < 0) { done = 4; break; }       // empty row: rejected at CSR build, cannot happen
+            const bool contested = O.j == B.j;
+            const bool won = !contested || B.bid > O.bid || (B.bid == O.bid && a == 0);
+            const bool owon = !contested || !won;
+            if ((lane == 0 && won) || (lane == 1 && owon)) {   // both warps store both commits (identical values)
+                SslapbBid Wb;
+                if (lane == 0) Wb = B; else { Wb.j = O.j; Wb.bid = O.bid; Wb.powner = O.powner; Wb.pdeg = O.pdeg; Wb.pstart = O.pstart; }
+                commit_win(P, lane == 0 ? me : O.me, lane == 0 ? st : O.st, lane == 0 ? dg : O.dg, Wb);
+            }
+            __syncwarp();
+            const int nme = won ? B.powner : me, ome = owon ? O.powner : O.me;
+            ++its; ++rounds;
+            if (its >= max_iter) done = 3;
+            if (nme >= 0 && ome >= 0) {                        // both slots stay live
+                if (won) { me = B.powner; st = B.pstart; dg = B.pdeg; cur = nxt; }
+                continue;                                      // lost: same person, same hot row, still in registers
+            }
+            nu = (nme >= 0) + (ome >= 0);
+            if (nme >= 0) { if (won) { me = B.powner; st = B.pstart; dg = B.pdeg; } }
+            else if (ome >= 0) { me = ome; st = owon ? O.pstart : O.st; dg = owon ? O.pdeg : O.dg; }
+            else me = -1;
+        }
+    }
+    return nu;
+}
+#endif
+
 // ---- long rows (more than one warp pass, e.g. dense inputs) in the single-bidder chain: the WHOLE CTA sweeps the row,
 // warp w taking the 32-chunk trips w, w+16, ...; the per-warp top-2 go through shared memory and warp 0 combines them,
 // commits and publishes the next bidder.  Two block barriers per round, independent of the row length up to 2048 entries
@@ -794,7 +1037,7 @@ __device__ __forceinline__ int coop_chain_rounds(const SslapbAuctionParams &P, d
 
 // CTA 0 finishes the eps-phase alone once nu <= t_small (nu only shrinks inside a phase).
 __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, SslapbCtrl *C, int nu, float eps_f,
-                                             long long its, long long max_iter, double pmin, double spread)
+                                             long long its, long long max_iter, double pmin, double spread, bool hot)
 {
     __shared__ int s_list[32], s_deg[32], s_j[32];
     __shared__ long long s_start[32];
@@ -812,6 +1055,10 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
     int li = -1, ldg = 0, done = 0;
     long long lst = 0;
     long long rw = 0, rs = 0;
+    int fell = 0;                                              // hot mode: bids of this warp the hot list could not decide
+#ifdef SSLAPB_LONG_ROWS
+    hot = false;                                               // (the long-row instance keeps the full-row loops)
+#endif
     if (tid == 0) { s_bounds[0] = pmin; s_bounds[1] = spread; }
     if (warp == 0) {
         if (lane < nu) {
@@ -848,6 +1095,10 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
         its = __shfl_sync(SSLAPB_FULL, s_its, 0);
     }
     // ---- 2..16 bidders: one warp per list position, distributed merge
+#ifndef SSLAPB_LONG_ROWS
+    if (nu > 1 && !done && hot) nu = multi_rounds_hot(P, eps, s_bounds, nu, s_list, s_start, s_deg, its, max_iter, done, rw, li, lst, ldg, fell);
+    else
+#endif
     if (nu > 1 && !done) nu = multi_rounds(P, eps, s_bounds, nu, s_list, s_start, s_deg, s_j, s_bidv, its, max_iter, done, rw, li, lst, ldg);
 
     unsigned long long tw1 = sslapb_globaltimer();
@@ -855,6 +1106,10 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
     // whenever the bidder's row is longer than one warp pass the whole CTA sweeps it (coop_chain_rounds)
     for (;;) {
         if (warp == 0) {
+#ifndef SSLAPB_LONG_ROWS
+            if (nu == 1 && !done && hot) nu = chain_rounds_hot(P, eps, s_bounds, li, lst, ldg, its, max_iter, done, rs, fell);
+            else
+#endif
             if (nu == 1 && !done) nu = chain_rounds(P, eps, li, lst, ldg, its, max_iter, done, rs);
             const bool longrow = nu == 1 && !done;             // chain_rounds stops in front of a long row
             if (lane == 0) {
@@ -880,7 +1135,9 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
         C->rounds_solo += s_rs;
         C->prof[3] += tw1 - tw0;
         C->prof[4] += sslapb_globaltimer() - tw1;
+        if (hot) C->hot_tail[0] += s_rw + s_rs;                // rounds run in hot form
     }
+    if (fell && lane == 0) atomicAdd((unsigned long long *)&C->hot_tail[1], (unsigned long long)fell);
 }
 
 // Block-wide exclusive prefix of a 0/1 flag over the threads of the CTA (in thread order); returns the CTA total in
@@ -975,7 +1232,7 @@ __device__ __forceinline__ bool cross_barrier(const SslapbAuctionParams &P, Ssla
 struct SslapbScope { int blk, nblk, gwarp, nwarps; bool lead; };   // CTA rank / count, warp rank / count, the one reporting thread
 __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, SslapbCtrl *C, const SslapbScope S, int nu, float eps_f,
                                              long long its, long long max_iter, double pmin, double spread, unsigned &bar_epoch,
-                                             unsigned &xround)
+                                             unsigned &xround, bool hot_mode)
 {
     __shared__ int s_red, s_tie;
     __shared__ int s_hpre[3];
@@ -1027,6 +1284,11 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
                             }
                         }
                     };
+    // Hot lists (hot.cu): in the first round of an eps-phase (every person bids) every row is tried — that is the probe
+    // which decides whether the rest of the phase, tail included, runs in hot form; afterwards only if it does.
+    const bool hot_probe = P.hot != nullptr && nu == P.N;
+    const bool hot_on = P.hot != nullptr && (hot_mode || hot_probe);
+    int n_hot_ok = 0, n_hot_fell = 0;
     // (a software pipeline across rows was measured to buy nothing: the sweep is instruction-issue bound)
     for (int a = S.gwarp; a < nu; a += S.nwarps) {
         int v = P.list[a];
@@ -1034,18 +1296,30 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
 #ifdef SSLAPB_SHARDED
         if (v < row_lo || v >= row_hi) continue;       // another rank's person (every rank still decodes every hole above)
 #endif
-        const long long st = __ldg(P.rowptr + v), en = __ldg(P.rowptr + v + 1);
-        int j; double bid;
-        if ((((en + 3) >> 2) - (st >> 2)) <= 32) {
-            const SslapbStreamChunk c = sslapb_stream_chunk(P.cols, P.vals, st, en, lane);
-            const SslapbBid o = row_bid_pruned(c, P.price, st, en, lane, eps, pmin, __ldg(P.rowmax + v) - spread, n2nd);
+        int j = -1; double bid = 0.0;
+        if (hot_on) {
+            const SslapbBid o = row_bid_hot(P.hot, P.rest, P.price, v, lane, eps);
             j = o.j; bid = o.bid;
-            // every candidate at -inf (objects priced +inf by single-choice bidders): the exact generic sweep decides
-            if (j < 0) row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);
-        } else {                                       // long row: multi-trip sweep, same bound pruning
-            row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid, pmin, __ldg(P.rowmax + v) - spread);
+            if (j >= 0) ++n_hot_ok; else ++n_hot_fell;
+        }
+        if (j < 0) {
+            const long long st = __ldg(P.rowptr + v), en = __ldg(P.rowptr + v + 1);
+            if ((((en + 3) >> 2) - (st >> 2)) <= 32) {
+                const SslapbStreamChunk c = sslapb_stream_chunk(P.cols, P.vals, st, en, lane);
+                const SslapbBid o = row_bid_pruned(c, P.price, st, en, lane, eps, pmin, __ldg(P.rowmax + v) - spread, n2nd);
+                j = o.j; bid = o.bid;
+                // every candidate at -inf (objects priced +inf by single-choice bidders): the exact generic sweep decides
+                if (j < 0) row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);
+            } else {                                   // long row: multi-trip sweep, same bound pruning
+                row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid, pmin, __ldg(P.rowmax + v) - spread);
+            }
         }
         emit_bid(a, j, bid);
+    }
+    if (hot_on && lane == 0 && (n_hot_ok | n_hot_fell)) {
+        atomicAdd((unsigned long long *)&C->hot_grid[0], (unsigned long long)n_hot_ok);
+        atomicAdd((unsigned long long *)&C->hot_grid[1], (unsigned long long)n_hot_fell);
+        if (hot_probe) atomicAdd(&C->hot_probe_fail, n_hot_fell);
     }
     if (n2nd && lane == 0) atomicAdd((unsigned long long *)&C->prune_second_pass, (unsigned long long)n2nd);
     if (S.lead) tp1 = sslapb_globaltimer();
@@ -1165,6 +1439,13 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
         C->its = its + 1;
         C->tie_flag = 0;
         C->rounds_grid += 1;
+        if (hot_probe) {                               // decisive for (nearly) everybody: the phase continues in hot form
+            int probed = P.N;
+#ifdef SSLAPB_SHARDED
+            if (sharded) probed = row_hi - row_lo;     // this rank swept only its own rows
+#endif
+            C->hot_mode = ((long long)C->hot_probe_fail * 16 < (long long)probed) ? 1 : 0;
+        }
         if (its + 1 >= max_iter) C->done = 3;
         tp5 = sslapb_globaltimer();
 #ifdef SSLAPB_SHARDED
@@ -1198,7 +1479,7 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
     const int nwarps = nblk * wpc;
     const int gtid = blockIdx.x * blockDim.x + tid;
     const int nthreads = nblk * blockDim.x;
-    __shared__ struct { int nu, done, nred, tie; float eps; long long its, max_iter; unsigned long long pmin0, pmin1, pmax; } s_top;
+    __shared__ struct { int nu, done, nred, tie, hot; float eps; long long its, max_iter; unsigned long long pmin0, pmin1, pmax; } s_top;
     unsigned bar_epoch = 0;                                    // barriers passed so far * #CTAs (wraps harmlessly)
     unsigned xround = P.xround_base;                           // row-sharded rounds of this communicator so far (all CTAs agree)
 
@@ -1214,6 +1495,7 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
             s_top.its = *(volatile long long *)&C->its;
             s_top.max_iter = *(volatile long long *)&C->max_iter;
             s_top.nred = *(volatile int *)&C->nreductions;
+            s_top.hot = *(volatile int *)&C->hot_mode;
             s_top.pmin0 = *(volatile unsigned long long *)&C->pmin_key[0];
             s_top.pmin1 = *(volatile unsigned long long *)&C->pmin_key[1];
             s_top.pmax = *(volatile unsigned long long *)&C->pmax_key;
@@ -1225,6 +1507,7 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
         const long long its = s_top.its;
         const long long max_iter = s_top.max_iter;
         const int phase_slot = s_top.nred & 1;
+        const bool hot_mode = __shfl_sync(SSLAPB_FULL, s_top.hot, 0) != 0;
         // price bounds for the pruned sweep, taken at the start of the eps-phase: pmin stays a valid lower bound all phase
         // long (prices never decrease); the spread is only a heuristic for which candidates to gather first
         const double pmin = sslapb_key2double(phase_slot ? s_top.pmin1 : s_top.pmin0);
@@ -1236,10 +1519,10 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
         if (nu > P.t_small) {
             // ================================ grid regime: one round ================================
             const SslapbScope S = {(int)blockIdx.x, (int)nblk, gwarp, nwarps, gtid == 0};
-            if (!spread_round(P, C, S, nu, eps_f, its, max_iter, pmin, spread, bar_epoch, xround)) return;
+            if (!spread_round(P, C, S, nu, eps_f, its, max_iter, pmin, spread, bar_epoch, xround, hot_mode)) return;
         } else {
             // ================================ warp-list regimes: CTA 0 finishes the phase ================================
-            if (blockIdx.x == 0) small_regime(P, C, nu, eps_f, its, max_iter, pmin, spread);
+            if (blockIdx.x == 0) small_regime(P, C, nu, eps_f, its, max_iter, pmin, spread, hot_mode && P.hot != nullptr);
             GB();
         }
 
@@ -1261,7 +1544,17 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
                 const int j = P.p2o[i];
                 const long long st = __ldg(P.rowptr + i), en = __ldg(P.rowptr + i + 1);
                 double vmax, choice, csum;
-                row_ece(P.cols, P.vals, P.price, st, en, lane, j, vmax, choice, csum);
+                if (P.hot) {
+                    // the sweep gathers every price of the row anyway: it also renews the bound of everything outside the
+                    // person's hot list, for the next eps-phase, and touches the hot row (L2-persisting window, api.cu)
+                    double rst;
+                    row_ece<true>(P.cols, P.vals, P.price, st, en, lane, j, vmax, choice, csum, P.hthr[i], &rst);
+                    if (lane == 0) P.rest[i] = rst;
+                    const int4 touch = __ldg(reinterpret_cast<const int4 *>(P.hot) + (long long)i * 32 + lane);
+                    asm volatile("" :: "r"(touch.x));
+                } else {
+                    row_ece(P.cols, P.vals, P.price, st, en, lane, j, vmax, choice, csum);
+                }
                 const double lhs = (choice - P.price[j]) + tol;
                 if (lhs < vmax - eps_t) viol = true;
             }
@@ -1298,6 +1591,7 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
                     C->pmin_key[phase_slot] = ~0ull;           // recycled two phases from now
                     C->nreductions += 1;
                     C->nu = P.N;
+                    C->hot_mode = 0; C->hot_probe_fail = 0;    // the next phase probes again
                 }
                 C->ece_viol = 0;
                 C->prof[5] += sslapb_globaltimer() - te0;
@@ -1440,7 +1734,10 @@ __global__ void __launch_bounds__(1024, 1) sslapb_bid_sweep_kernel(SslapbAuction
 __global__ void sslapb_auction_init_kernel(SslapbAuctionParams P, int warm)
 {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, n = gridDim.x * blockDim.x;
-    for (int i = gtid; i < P.N; i += n) { P.p2o[i] = -1; P.list[i] = i; }
+    for (int i = gtid; i < P.N; i += n) {
+        P.p2o[i] = -1; P.list[i] = i;
+        if (P.rest) P.rest[i] = __longlong_as_double(0x7ff0000000000000ll);   // no bound yet: the first eps-CS sweep writes it
+    }
     for (int j = gtid; j < P.M; j += n) {
         const double p0 = warm ? P.price[j] : 0.0;
         SslapbObjRec r; r.start = 0; r.owner = -1; r.deg = 0; r.price = p0; r.pad = 0;

@@ -38,6 +38,17 @@ struct SslapbCtrl {
     unsigned long long sharded_ns;                     // ... ns of those rounds in total (CTA 0 view)
     unsigned long long sweep_ns[2];                    // in-situ bidding step of full-frontier rounds (nu == N): total ns / count
     double tol;                                        // eps-CS tolerance of eCE_satisfied (1e-7, auction_.pyx:16; 0 in strict mode)
+    // ---- hot lists (hot.cu)
+    int hot_mode;                                      // this eps-phase decides bids from the hot lists first (set by the probing round)
+    int hot_probe_fail;                                // bids of the phase's first round (every person bids) the hot list could not decide
+    long long hot_grid[2], hot_tail[2];                // instrumentation: bids decided by the hot list / handed to the full-row sweep
+};
+
+// One hot-list entry (hot.cu): 32 per person, 512 bytes per row, lane t of a warp reads entry t.
+struct __align__(16) SslapbHotEnt {
+    int col;                  // object, -1 = padding
+    int idx;                  // index of the entry inside its CSR row (tie rule: the LAST maximal entry wins, auction_.pyx:351)
+    double a;                 // value (sign-folded)
 };
 
 // Per-object record (32 B = one sector): everything a bidder needs to know about the object it wins, so that the
@@ -59,6 +70,9 @@ struct SslapbAuctionParams {
     const double *vals;       // sign-folded values ('min' negated, :236-237); same alignment/slack
     const double *rowmax;     // per person: max_j a_ij (static; the pruned sweeps gather only entries within the price
                               // spread of it)
+    const SslapbHotEnt *hot;  // hot lists (hot.cu): the 32 largest entries of every row; nullptr = off
+    const double *hthr;       // per person: entries with a <= hthr are NOT in the hot list (NaN: every entry is)
+    double *rest;             // per person: upper bound of a_ik - p_k over the entries outside the hot list (+inf: unknown)
     double *price;            // p (:220)
     SslapbObjRec *rec;        // per-object record incl. object_to_person (:232)
     int *p2o;                 // person_to_object (:231)

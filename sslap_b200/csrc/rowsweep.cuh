@@ -308,6 +308,51 @@ __device__ __forceinline__ SslapbBid row_bid_pruned_lean(const SslapbStreamChunk
     return o;
 }
 
+// Bid of one person from its hot list (hot.cu): lane t holds hot entry t; one price gather per lane, no per-lane
+// tournament.  Exact when the second-best value found is strictly above `rest` (the bound of everything outside the
+// list), or when nothing is outside (rest = -inf); otherwise j = -1 sends the caller to the full-row sweep.
+__device__ __forceinline__ SslapbBid row_bid_hot(const SslapbHotEnt *__restrict__ hot, const double *rest_arr, const double *price,
+                                                 int person, int lane, double eps)
+{
+    const int4 q = __ldg(reinterpret_cast<const int4 *>(hot) + (long long)person * 32 + lane);
+    const double rest = rest_arr[person];
+    const double a = __hiloint2double(q.w, q.z);
+    double v = SSLAPB_NEG_INF;
+    if (q.x >= 0) v = a - price[q.x];
+    const bool has = v > SSLAPB_NEG_INF;                       // real -inf candidates: left to the generic sweep
+    const unsigned long long bk = has ? sslapb_key_of(v) : 0ull;
+    const unsigned bh = (unsigned)(bk >> 32), bl = (unsigned)bk;
+    const unsigned khi = __reduce_max_sync(SSLAPB_FULL, bh);
+    const unsigned hm = __ballot_sync(SSLAPB_FULL, (bh == khi) & has);
+    bool iswin;
+    unsigned own;
+    if (__popc(hm) <= 1) {                                     // one lane holds the maximal high word: it is the winner
+        own = hm;
+        iswin = (hm >> lane) & 1u;
+    } else {
+        const unsigned klo = __reduce_max_sync(SSLAPB_FULL, bh == khi ? bl : 0u);
+        const bool top = (bh == khi) & (bl == klo) & has;
+        const int widx = __reduce_max_sync(SSLAPB_FULL, top ? q.y : -1);   // equal values: the later row entry wins (:351)
+        iswin = top & (q.y == widx);
+        own = __ballot_sync(SSLAPB_FULL, iswin);
+    }
+    const unsigned long long cand = iswin ? 0ull : bk;         // one candidate per lane: the second best is the best of the others
+    const unsigned chh = (unsigned)(cand >> 32), chl = (unsigned)cand;
+    const unsigned shi = __reduce_max_sync(SSLAPB_FULL, chh);
+    const unsigned slo = __reduce_max_sync(SSLAPB_FULL, chh == shi ? chl : 0u);
+    const unsigned long long skey = ((unsigned long long)shi << 32) | slo;
+    const int src = own ? (__ffs(own) - 1) : lane;
+    const double bc = __shfl_sync(SSLAPB_FULL, a, src);
+    const int bj = __shfl_sync(SSLAPB_FULL, q.x, src);
+    const double wi = skey > SSLAPB_KEY_NEG_INF ? sslapb_key2double(skey) : SSLAPB_NEG_INF;   // :344
+    SslapbBid o;
+    o.powner = -1; o.pdeg = 0; o.pstart = 0;
+    o.bid = (bc - wi) + eps;                                   // :360
+    const bool proven = (wi > rest) || (rest == SSLAPB_NEG_INF);
+    o.j = (own && proven) ? bj : -1;
+    return o;
+}
+
 template <int W>
 __device__ __forceinline__ void row_bid(const int *__restrict__ cols, const double *__restrict__ vals,
                                         const double *price, long long start, long long end, int t, double eps,
@@ -333,13 +378,16 @@ __device__ __noinline__ SslapbBid row_bid_rec(const int *__restrict__ cols, cons
 //   vmax   = max_k (a_ik - p_k)
 //   choice = value of the LAST entry whose column is jsel (:467-471)
 //   csum   = sum of the values of ALL entries whose column is jsel (get_obj adds every match, :514-521)
+//   REST: additionally rest = max_k (a_ik - p_k) over the entries with a_ik <= hthr — the entries outside the person's
+//   hot list (hot.cu); -inf when there is none
+template <bool REST = false>
 __device__ __forceinline__ void row_ece(const int *__restrict__ cols, const double *__restrict__ vals,
                                         const double *price, long long start, long long end, int lane, int jsel,
-                                        double &vmax, double &choice, double &csum)
+                                        double &vmax, double &choice, double &csum, double hthr = 0.0, double *rest = nullptr)
 {
     const int4 *c4 = reinterpret_cast<const int4 *>(cols);
     const double2 *v2 = reinterpret_cast<const double2 *>(vals);
-    double vm = SSLAPB_NEG_INF, ch_v = 0.0, cs = 0.0;
+    double vm = SSLAPB_NEG_INF, ch_v = 0.0, cs = 0.0, rm = SSLAPB_NEG_INF;
     int ch_i = -1;
     const long long c0 = start >> 2, c1 = (end + 3) >> 2;
     const int trips = __shfl_sync(SSLAPB_FULL, (int)((c1 - c0 + 31) / 32), 0);
@@ -358,6 +406,7 @@ __device__ __forceinline__ void row_ece(const int *__restrict__ cols, const doub
             if (e >= start && e < end) {
                 const double v = vv[k] - price[cc[k]];
                 vm = fmax(vm, v);
+                if (REST && vv[k] <= hthr) rm = fmax(rm, v);
                 if (cc[k] == jsel) { ch_v = vv[k]; ch_i = (int)(e - start); cs += vv[k]; }
             }
         }
@@ -369,7 +418,9 @@ __device__ __forceinline__ void row_ece(const int *__restrict__ cols, const doub
         const double ov = __shfl_xor_sync(SSLAPB_FULL, ch_v, off);
         if (oi > ch_i) { ch_i = oi; ch_v = ov; }
         cs += __shfl_xor_sync(SSLAPB_FULL, cs, off);
+        if (REST) rm = fmax(rm, __shfl_xor_sync(SSLAPB_FULL, rm, off));
     }
+    if (REST) *rest = rm;
     vmax = vm; choice = ch_v; csum = cs;
 }
 

@@ -109,9 +109,9 @@ def test_bid_sweep_kernel_bit_exact(gpu, oracle_mod):
 
 
 def test_bid_sweep_streamed_bit_exact(gpu, oracle_mod):
-    """Full-frontier sweep through the software-pipelined kernel (default), the TMA-ring kernel (merge bit 2) and the
-    round-1 per-row kernel (bit 3): all bit-exact against the oracle, with and without bound pruning, incl. long rows, a
-    rectangular problem and +inf prices."""
+    """Full-frontier sweep through every variant of the kernel — per-row (default), TMA ring (merge bit 2), software-pipelined
+    (bit 3, with its CTA sizes) and four rows per warp (bit 7): all bit-exact against the oracle, with and without bound
+    pruning, incl. long rows, a rectangular problem and +inf prices."""
     sslap_b200, nat, h = gpu
     L = nat.load()
     cases = [(1000, 0.01, "int", 3, None), (3000, 0.4, "float", 6, None), (20000, 0.0002, "float", 7, None),
@@ -131,7 +131,7 @@ def test_bid_sweep_streamed_bit_exact(gpu, oracle_mod):
                 prices = rng.uniform(0, 5, M)
                 prices[rng.integers(0, M, max(1, M // 50))] = np.inf
             oj, ob = oracle_mod.bid_sweep(rowptr, loc[:, 1], -val, prices, np.arange(n, dtype=np.int32), 0.37)
-            for merge in (0, 2, 4, 6, 128, 130, 8, 10, 8 | 16, 8 | 32 | 2, 8 | 48, 8 | 64):   # 4-rows/warp (default), TMA ring, per-row, pipelined
+            for merge in (0, 2, 4, 6, 128, 130, 8, 10, 8 | 16, 8 | 32 | 2, 8 | 48, 8 | 64):   # per-row (default), TMA ring, 4 rows/warp, pipelined
                 jb = np.empty(n, dtype=np.int32)
                 bd = np.empty(n, dtype=np.float64)
                 ms = C.c_float(0)

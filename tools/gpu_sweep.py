@@ -18,8 +18,8 @@ n = 100000
 loc, val = make_problem(n, 0.001, "float", seed=0)
 sslap_b200.auction_solve(loc=loc, val=val, size=(n, n), cardinality_check=False)
 by = 12 * val.size + 36 * n
-variants = [("4 rows/warp, 8 lanes/row (default)", 1), ("4 rows/warp, pruning off", 3),
-            ("per-row kernel (round 1)", 1 | 128), ("per-row kernel, pruning off", 3 | 128),
+variants = [("4 rows/warp, 8 lanes/row", 1 | 128), ("4 rows/warp, pruning off", 3 | 128),
+            ("per-row kernel (default)", 1), ("per-row kernel, pruning off", 3),
             ("pipelined per-row 768 thr", 1 | 8), ("pipelined per-row 1024 thr", 1 | 8 | 16), ("TMA ring", 1 | 4)]
 for rep in range(2):
     for name, merge in variants:
