@@ -84,6 +84,7 @@ typedef struct sslapb_meta {
     /* ---- ABI version 3: hot lists (the 32 largest entries of every row decide a bid when that is provably exact) */
     int64_t hot_grid_bids, hot_grid_fallbacks;   /* grid-regime bids decided by the hot list / handed on to the full-row sweep */
     int64_t hot_tail_rounds, hot_tail_fallbacks; /* few-bidder + chain rounds run in hot form / their bids handed on to the full row */
+    int64_t rounds_nohole;   /* rounds (of rounds_grid) that found no unowned object and no equal bids: no compaction, no final barrier */
 } sslapb_meta;
 
 int  sslapb_create(int device, sslapb_handle **out);
@@ -101,6 +102,7 @@ int    sslapb_abi_version(void);
    device-resident loop; A/B runs; default 0),
    "batch_v1" (1: round 1's batch kernel — a whole warp sweeps one bidder at a time — instead of the sub-warp kernel; A/B runs),
    "hot" (0: never decide bids from the hot lists — A/B runs; default 1),
+   "l2_persist" (0: no persisting L2 access-policy window over the hot lists during a solve — A/B runs; default 1),
    "coop" (row-sharded solves only; 0: launch the persistent kernel without the cooperative attribute so that several of them
    can run side by side on ONE GPU — the driver runs one cooperative kernel at a time; only for the virtual-rank test, default 1),
    "strict" (1: strict-optimality stop rule — eps-CS is tested with eps = 1/(N+1) and zero tolerance and the eps schedule runs

@@ -38,7 +38,7 @@ class Meta(C.Structure):
                 ("sweep_insitu_us", C.c_float), ("sweep_insitu_n", C.c_int32), ("warm_start", C.c_int32),
                 ("strict", C.c_int32),
                 ("hot_grid_bids", C.c_int64), ("hot_grid_fallbacks", C.c_int64),
-                ("hot_tail_rounds", C.c_int64), ("hot_tail_fallbacks", C.c_int64)]
+                ("hot_tail_rounds", C.c_int64), ("hot_tail_fallbacks", C.c_int64), ("rounds_nohole", C.c_int64)]
 
 
 _lib = None

@@ -119,6 +119,7 @@ struct sslapb_handle {
     int strict = 0;                // strict-optimality stop rule (see the header)
     int coop = 1;                  // 0: launch the row-sharded persistent kernel without the cooperative attribute (virtual ranks)
     int hot = 1;                   // hot lists (hot.cu): 0 = off (A/B runs)
+    int l2_persist = 1;            // 1: L2 access-policy window (persisting) over the hot lists during a solve; 0 = off (A/B runs)
     size_t l2_persist_max = 0;     // cudaDevAttrMaxPersistingL2CacheSize
     int l2_window_max = 0;         // cudaDevAttrMaxAccessPolicyWindowSize
     // warm start: prices for the next solve (sslapb_set_prices)
@@ -193,7 +194,6 @@ extern "C" int sslapb_create(int device, sslapb_handle **out)
         cudaDeviceGetAttribute(&pmax, cudaDevAttrMaxPersistingL2CacheSize, device);
         cudaDeviceGetAttribute(&wmax, cudaDevAttrMaxAccessPolicyWindowSize, device);
         h->l2_persist_max = (size_t)(pmax > 0 ? pmax : 0); h->l2_window_max = wmax > 0 ? wmax : 0;
-        if (pmax > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)pmax);
         cudaGetLastError();
     }
     if ((e = sslapb_hk_persistent_grid(device, &h->hk_grid)) != cudaSuccess) { delete h; return -(int)e; }
@@ -235,6 +235,7 @@ extern "C" int sslapb_set_option(sslapb_handle *h, const char *name, int64_t val
     if (!strcmp(name, "strict")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->strict = (int)value; return 0; }
     if (!strcmp(name, "hk_host_loop")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->hk_host_loop = (int)value; return 0; }
     if (!strcmp(name, "batch_v1")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->batch_v1 = (int)value; return 0; }
+    if (!strcmp(name, "l2_persist")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->l2_persist = (int)value; return 0; }
     if (!strcmp(name, "hot")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->hot = (int)value; return 0; }
     if (!strcmp(name, "coop")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->coop = (int)value; return 0; }
     return fail(h, SSLAPB_E_BAD_ARG, std::string("unknown option ") + name);
@@ -537,10 +538,12 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
         SslapbHotEnt *hot = reinterpret_cast<SslapbHotEnt *>(hb + head);
         P.hot = hot;
         CK(sslapb_launch_hot_build(P.rowptr, P.cols, P.vals, N, hot, const_cast<double *>(P.hthr), h->sms, h->stream));
-        if (h->l2_persist_max > 0 && h->l2_window_max > 0) {   // loads from the hot lists (and rest[]) stay in L2 across the phase
+        if (h->l2_persist && h->l2_persist_max > 0 && h->l2_window_max > 0) {   // loads from the hot lists (and rest[]) stay in L2 across the phase
             cudaStreamAttrValue av;
             memset(&av, 0, sizeof av);
             const size_t win = total < (size_t)h->l2_window_max ? total : (size_t)h->l2_window_max;
+            // the set-aside is taken from the ordinary L2 for as long as the limit stands: only while this solve runs
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, win < h->l2_persist_max ? win : h->l2_persist_max);
             av.accessPolicyWindow.base_ptr = hb;
             av.accessPolicyWindow.num_bytes = win;
             av.accessPolicyWindow.hitRatio = win <= h->l2_persist_max ? 1.0f : (float)((double)h->l2_persist_max / (double)win);
@@ -581,7 +584,7 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
     CK(cudaMemcpyAsync(chosen.data(), P.chosen, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&c, P.ctrl, sizeof c, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (l2_window) { cudaCtxResetPersistingL2Cache(); cudaGetLastError(); }
+    if (l2_window) { cudaCtxResetPersistingL2Cache(); cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0); cudaGetLastError(); }
     if (sharded) {
         h->xround += (unsigned)c.rounds_sharded;
         if (c.abort_flag) h->comm_broken = true;               // the ranks may have left the solve at different rounds
@@ -624,6 +627,7 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
         meta->warm_start = warm ? 1 : 0; meta->strict = h->strict;
         meta->hot_grid_bids = c.hot_grid[0]; meta->hot_grid_fallbacks = c.hot_grid[1];
         meta->hot_tail_rounds = c.hot_tail[0]; meta->hot_tail_fallbacks = c.hot_tail[1];
+        meta->rounds_nohole = c.rounds_nohole;
         (void)assigned;
     }
     return SSLAPB_OK;

@@ -689,8 +689,14 @@ __device__ __forceinline__ int multi_rounds_hot(const SslapbAuctionParams &P, do
         if (lane < nu) O = s_hpub[par][lane];
         par ^= 1;
         if (__any_sync(SSLAPB_FULL, lane < nu && O.j < 0)) { done = 4; break; }   // empty row: rejected at CSR build
+        // who is beaten (:375-385): only positions that share their object with another one can be (inactive lanes carry
+        // unique negative ids), and most rounds have none
         bool beaten = false;
-        for (int c = 0; c < nu; ++c) {
+        const unsigned peers = __match_any_sync(SSLAPB_FULL, O.j);
+        unsigned contested = __ballot_sync(SSLAPB_FULL, peers != (1u << lane));
+        while (contested) {
+            const int c = __ffs(contested) - 1;
+            contested &= contested - 1u;
             const int cj = __shfl_sync(SSLAPB_FULL, O.j, c);
             const double cb = __shfl_sync(SSLAPB_FULL, O.bid, c);
             beaten |= (c != lane) && (cj == O.j) && (cb > O.bid || (cb == O.bid && c < lane));
@@ -1230,7 +1236,11 @@ __device__ __forceinline__ bool cross_barrier(const SslapbAuctionParams &P, Ssla
 
 // One Jacobi round with the bidders spread over all CTAs of the grid (auction_.pyx:337-430).
 struct SslapbScope { int blk, nblk, gwarp, nwarps; bool lead; };   // CTA rank / count, warp rank / count, the one reporting thread
-__device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, SslapbCtrl *C, const SslapbScope S, int nu, float eps_f,
+// Returns 0 = aborted, 1 = round done behind a final grid barrier (the caller re-reads the control block), 2 = round done
+// WITHOUT that barrier: no bidder found an unowned object (no hole, so the list keeps its size and order and nothing is
+// compacted) and no equal bids were seen (tie_flag stays 0) — every CTA knows the next round's inputs (same nu, its + 1)
+// and nothing is written after the third barrier that the next round reads.  67 % of the grid rounds of a C3 solve.
+__device__ __forceinline__ int spread_round(const SslapbAuctionParams &P, SslapbCtrl *C, const SslapbScope S, int nu, float eps_f,
                                              long long its, long long max_iter, double pmin, double spread, unsigned &bar_epoch,
                                              unsigned &xround, bool hot_mode)
 {
@@ -1289,6 +1299,26 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
     const bool hot_probe = P.hot != nullptr && nu == P.N;
     const bool hot_on = P.hot != nullptr && (hot_mode || hot_probe);
     int n_hot_ok = 0, n_hot_fell = 0;
+    // end of round, lead thread: hot form on/off for the rest of the phase.  The probing round decides first (optimistic:
+    // its bounds are as fresh as they get), afterwards the share of bids the hot lists failed to decide since the last look.
+    auto hot_bookkeeping = [&]() {
+        if (P.hot == nullptr) return;
+        const long long ok = *(volatile long long *)&C->hot_grid[0], fl = *(volatile long long *)&C->hot_grid[1];
+        if (hot_probe) {
+            int probed = P.N;
+#ifdef SSLAPB_SHARDED
+            if (P.nranks > 1 && nu > P.t_shard) probed = __ldg(P.rowsplit + P.rank + 1) - __ldg(P.rowsplit + P.rank);   // own rows only
+#endif
+            C->hot_mode = ((long long)C->hot_probe_fail * 16 < (long long)probed) ? 1 : 0;
+            C->hot_last[0] = ok; C->hot_last[1] = fl;
+        } else if (hot_mode) {
+            const long long d = (ok + fl) - (C->hot_last[0] + C->hot_last[1]), df = fl - C->hot_last[1];
+            if (d >= 64) {
+                if (df * 8 > d) C->hot_mode = 0;
+                C->hot_last[0] = ok; C->hot_last[1] = fl;
+            }
+        }
+    };
     // (a software pipeline across rows was measured to buy nothing: the sweep is instruction-issue bound)
     for (int a = S.gwarp; a < nu; a += S.nwarps) {
         int v = P.list[a];
@@ -1325,7 +1355,7 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
     if (S.lead) tp1 = sslapb_globaltimer();
 #ifdef SSLAPB_SHARDED
     if (sharded) {
-        if (!cross_barrier(P, C, (unsigned)S.nblk, bar_epoch, xk)) return false;
+        if (!cross_barrier(P, C, (unsigned)S.nblk, bar_epoch, xk)) return 0;
         // merge (:375-385) over ALL nu bids, identically on every rank
         for (int a = blockIdx.x * blockDim.x + tid; a < nu; a += S.nblk * blockDim.x) {
             const int j = bidj[a];
@@ -1339,7 +1369,7 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
         }
     }
 #endif
-    if (!grid_barrier(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return false;
+    if (!grid_barrier(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return 0;
     if (S.lead) {
         tp2 = sslapb_globaltimer();
         // in-situ full-frontier bidding step (every person bids: first round of an eps-phase), up to the barrier that
@@ -1356,7 +1386,7 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
             const int j = bidj[a];
             if (P.bidkey[j] == sslapb_ord64(bidv[a])) atomicMin(P.winpos + j, a);
         }
-        if (!grid_barrier(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return false;
+        if (!grid_barrier(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return 0;
     }
     // (2) assignment (:394-427), by the winner's own list position
     int myholes = 0;
@@ -1385,7 +1415,7 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
     __syncthreads();
     if (tid == 0) P.hole_count[S.blk] = s_red;
     if (S.lead) tp3 = sslapb_globaltimer();
-    if (!grid_barrier(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return false;
+    if (!grid_barrier(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return 0;
     if (S.lead) tp4 = sslapb_globaltimer();
     // (3) push_all_left (:137-162): k-th hole left of new_nu <- k-th live entry right of it
     if (warp == 0) {                                   // per-CTA hole counts -> total, my prefix, prefix of the split chunk
@@ -1409,6 +1439,22 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
     }
     __syncthreads();
     const int H = __shfl_sync(SSLAPB_FULL, s_hpre[2], 0), hpre = __shfl_sync(SSLAPB_FULL, s_hpre[1], 0);
+    if (H == 0 && !tie && !hot_probe && its + 2 < max_iter) {  // no hole, no tie: nothing to compact, nothing to reset
+        if (S.lead) {
+            C->its = its + 1;
+            C->rounds_grid += 1;
+            C->rounds_nohole += 1;
+            hot_bookkeeping();
+            tp5 = sslapb_globaltimer();
+#ifdef SSLAPB_SHARDED
+            if (sharded) { C->rounds_sharded += 1; C->sharded_ns += tp5 - tp0; }
+#endif
+            C->prof[0] += tp1 - tp0; C->prof[1] += tp3 - tp2; C->prof[2] += tp5 - tp4;
+            C->prof[7] += (tp2 - tp1) + (tp4 - tp3);
+        }
+        __syncthreads();                               // s_hpre / s_red / s_tie are rewritten by the next round
+        return 2;
+    }
     const int new_nu = nu - H;
     const int cb = new_nu / L;                         // chunk that contains the split point
     int cnt = 0;
@@ -1439,26 +1485,20 @@ __device__ __forceinline__ bool spread_round(const SslapbAuctionParams &P, Sslap
         C->its = its + 1;
         C->tie_flag = 0;
         C->rounds_grid += 1;
-        if (hot_probe) {                               // decisive for (nearly) everybody: the phase continues in hot form
-            int probed = P.N;
-#ifdef SSLAPB_SHARDED
-            if (sharded) probed = row_hi - row_lo;     // this rank swept only its own rows
-#endif
-            C->hot_mode = ((long long)C->hot_probe_fail * 16 < (long long)probed) ? 1 : 0;
-        }
+        hot_bookkeeping();
         if (its + 1 >= max_iter) C->done = 3;
         tp5 = sslapb_globaltimer();
 #ifdef SSLAPB_SHARDED
         if (sharded) { C->rounds_sharded += 1; C->sharded_ns += tp5 - tp0; }
 #endif
     }
-    if (!grid_barrier(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return false;
+    if (!grid_barrier(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return 0;
     if (S.lead) {
         C->prof[0] += tp1 - tp0; C->prof[1] += tp3 - tp2; C->prof[2] += tp5 - tp4;
         C->prof[7] += (tp2 - tp1) + (tp4 - tp3) + (sslapb_globaltimer() - tp5);
     }
     }
-    return true;
+    return 1;
 }
 
 #define GB() do { if (!grid_barrier(C, nblk, bar_epoch, P.watchdog_ns)) return; } while (0)
@@ -1519,7 +1559,13 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
         if (nu > P.t_small) {
             // ================================ grid regime: one round ================================
             const SslapbScope S = {(int)blockIdx.x, (int)nblk, gwarp, nwarps, gtid == 0};
-            if (!spread_round(P, C, S, nu, eps_f, its, max_iter, pmin, spread, bar_epoch, xround, hot_mode)) return;
+            long long its_l = its;
+            for (;;) {
+                const int r = spread_round(P, C, S, nu, eps_f, its_l, max_iter, pmin, spread, bar_epoch, xround, hot_mode);
+                if (r == 0) return;
+                if (r == 1) break;
+                ++its_l;                                       // r == 2: same frontier, next round straight away
+            }
         } else {
             // ================================ warp-list regimes: CTA 0 finishes the phase ================================
             if (blockIdx.x == 0) small_regime(P, C, nu, eps_f, its, max_iter, pmin, spread, hot_mode && P.hot != nullptr);

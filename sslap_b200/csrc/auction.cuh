@@ -42,6 +42,8 @@ struct SslapbCtrl {
     int hot_mode;                                      // this eps-phase decides bids from the hot lists first (set by the probing round)
     int hot_probe_fail;                                // bids of the phase's first round (every person bids) the hot list could not decide
     long long hot_grid[2], hot_tail[2];                // instrumentation: bids decided by the hot list / handed to the full-row sweep
+    long long hot_last[2];                             // hot_grid[] at the lead thread's last look (adaptive on/off)
+    long long rounds_nohole;                           // grid rounds that ended without compaction and final barrier (no hole, no tie)
 };
 
 // One hot-list entry (hot.cu): 32 per person, 512 bytes per row, lane t of a warp reads entry t.

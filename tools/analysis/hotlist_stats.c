@@ -13,6 +13,7 @@ static void stats_bid(const void *s, int nb, int i, double vbest, double wi, int
 static const int HS[NH] = {8, 16, 24, 32};
 static double *g_hmin[NH];
 static double g_pmin;
+static int g_prev_nb = -1; static long long g_grid_rounds, g_grid_same, g_hist_same[8], g_hist_all[8];
 static long long g_ph_h[64][NH];
 static double *g_restR; static long long g_ph_tail[64], g_ph_pass[64], g_ph_passR[64], g_ph_chain[64], g_ph_chain_pass[64];
 static int *g_seen; static int g_phase; static long long g_tail_first;
@@ -79,6 +80,14 @@ static void stats_bid(const void *sv, int nb, int i, double vbest, double wi, in
             g_restR[i] = m;
         }
     }
+    if (i == s->unassigned[0]) {                     /* first bid of a round */
+        if (g_prev_nb > 32) {
+            int b = g_prev_nb <= 128 ? 0 : g_prev_nb <= 512 ? 1 : g_prev_nb <= 2048 ? 2 : g_prev_nb <= 8192 ? 3 : 4;
+            ++g_grid_rounds; ++g_hist_all[b];
+            if (nb == g_prev_nb) { ++g_grid_same; ++g_hist_same[b]; }
+        }
+        g_prev_nb = nb;
+    }
     const int tail = nb <= 32;
     for (int h = 0; h < NH; ++h) {
         if (tail) { g_tailS[h] += wi > g_restS[h][i]; g_tailD[h] += wi > g_restD[h][i]; }
@@ -94,6 +103,8 @@ static void stats_bid(const void *sv, int nb, int i, double vbest, double wi, in
 
 void stats_report(void)
 {
+    printf("grid rounds %lld, of which the frontier size did not change (no hole): %lld\n", g_grid_rounds, g_grid_same);
+    for (int b = 0; b < 5; ++b) printf("  frontier bucket %d: rounds %lld no-hole %lld\n", b, g_hist_all[b], g_hist_same[b]);
     for (int p = 1; p <= g_phase; ++p) printf("phase %2d: tail bids %8lld  pass(static32) %.4f  pass(with refresh) %.4f   chain bids %8lld pass(refresh) %.4f\n", p, g_ph_tail[p], (double)g_ph_pass[p] / (g_ph_tail[p] ? g_ph_tail[p] : 1), (double)g_ph_passR[p] / (g_ph_tail[p] ? g_ph_tail[p] : 1), g_ph_chain[p], (double)g_ph_chain_pass[p] / (g_ph_chain[p] ? g_ph_chain[p] : 1));
     for (int p = 1; p <= g_phase; ++p) printf("phase %2d static H=8/16/24/32: %.4f %.4f %.4f %.4f\n", p, (double)g_ph_h[p][0] / (g_ph_tail[p] ? g_ph_tail[p] : 1), (double)g_ph_h[p][1] / (g_ph_tail[p] ? g_ph_tail[p] : 1), (double)g_ph_h[p][2] / (g_ph_tail[p] ? g_ph_tail[p] : 1), (double)g_ph_h[p][3] / (g_ph_tail[p] ? g_ph_tail[p] : 1));
     printf("tail bids whose person bids for the first time in this phase's tail: %lld (phases %d)\n", g_tail_first, g_phase);

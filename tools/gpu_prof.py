@@ -19,7 +19,7 @@ def run(tag, n, d, reps=2, **kw):
         print(f"[{tag}] its={m.its} rounds g/w/s={m.rounds_grid}/{m.rounds_warp}/{m.rounds_solo} solve={m.solve_ms:.2f}ms "
               f"setup={m.setup_ms:.2f} h2d={m.h2d_ms:.2f} wall={w*1e3:.1f}ms 2nd_pass_rows={m.prune_second_pass}", flush=True)
         print("    " + "  ".join(f"{k}={v:.2f}ms" for k, v in zip(names, m.prof_ms)))
-        print(f"    hot lists: grid bids {m.hot_grid_bids} (+{m.hot_grid_fallbacks} handed to the full row)  tail rounds {m.hot_tail_rounds} (bids handed on: {m.hot_tail_fallbacks})")
+        print(f"    hot lists: grid bids {m.hot_grid_bids} (+{m.hot_grid_fallbacks} handed to the full row)  tail rounds {m.hot_tail_rounds} (bids handed on: {m.hot_tail_fallbacks})  no-hole grid rounds {m.rounds_nohole}")
         per = lambda t, c: (1e3 * t / c) if c else 0.0
         print(f"    per-round us: grid={per(m.prof_ms[0]+m.prof_ms[1]+m.prof_ms[2]+m.prof_ms[7], m.rounds_grid):.2f} "
               f"(barriers {per(m.prof_ms[7], m.rounds_grid):.2f}) warp={per(m.prof_ms[3], m.rounds_warp):.2f} solo={per(m.prof_ms[4], m.rounds_solo):.2f}", flush=True)
@@ -30,6 +30,7 @@ if which in ("c2", "both"):
 if which in ("c3", "both"):
     loc, val = run("C3", 100000, 0.001)
     h.set_option("hot", 0); run("C3 hot off", 100000, 0.001, reps=1); h.set_option("hot", 1)
+    h.set_option("l2_persist", 0); run("C3 hot on, no L2 window", 100000, 0.001, reps=2); h.set_option("l2_persist", 1)
     n = 100000
     for merge in (1, 3):
         for flush in (0, 1):
