@@ -41,6 +41,8 @@ cudaError_t sslapb_launch_bid_sweep_tma(const SslapbAuctionParams *, const int *
 cudaError_t sslapb_launch_price_bounds(const SslapbAuctionParams *, cudaStream_t);
 cudaError_t sslapb_launch_bid_sweep2(const SslapbAuctionParams *, const int *, int, float, int, int, int, int, cudaStream_t);
 cudaError_t sslapb_launch_bid_sweep4(const SslapbAuctionParams *, const int *, int, float, int, int, cudaStream_t);
+cudaError_t sslapb_launch_bid_sweep_hot(const SslapbAuctionParams *, const int *, int, float, int, int, cudaStream_t);
+cudaError_t sslapb_launch_hot_rest(const SslapbAuctionParams *, int, cudaStream_t);
 cudaError_t sslapb_hk_launch_greedy(const long long *, const int *, int, int *, int *, SslapbHkFlags *, int, cudaStream_t);
 cudaError_t sslapb_hk_launch_phase_init(int, int, const int *, int *, int *, int *, int *, SslapbHkFlags *, int, cudaStream_t);
 cudaError_t sslapb_hk_launch_bfs_level(const long long *, const int *, int, int, const int *, int *, int *, int *, int *,
@@ -142,6 +144,7 @@ struct sslapb_handle {
     bool has_vals = false;
     DevBuf stage_idx, stage_val, stage_mat, cols, vals, rowptr, rowmax, flags;
     DevBuf hotbuf;                 // rest[N] | hthr[N] | hot lists N x 512 B (one allocation: one L2 access-policy window covers it)
+    bool hot_valid = false;        // hotbuf holds the lists of the resident CSR
     DevBuf sort_keys, sort_idx, sort_hist, sort_rows, sort_cols, sort_val;   // only for unsorted input
     DevBuf b_off, b_rows, b_cols, b_eps, b_meta, b_bad, b_rec;               // batched problems
     int batch_v1 = 0;              // option "batch_v1": 1 = round 1's batch kernel (whole warp per bidder), A/B runs
@@ -311,7 +314,7 @@ static int build_from_coo(sslapb_handle *h, const void *rows, const void *cols, 
     CK(cudaEventRecord(h->ev[2], h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (nnz == 0) F.empty_rows = 1;
-    h->N = n_rows; h->M = n_cols; h->nnz = nnz; h->has_vals = val != nullptr;
+    h->N = n_rows; h->M = n_cols; h->nnz = nnz; h->has_vals = val != nullptr; h->hot_valid = false;
     if (F.out_of_range) return fail(h, SSLAPB_E_OUT_OF_RANGE, "loc holds an index outside the matrix");
     if (F.unsorted) {
         // The reference silently requires row-sorted input (auction_.pyx:33-48).  Superset behaviour: stable device
@@ -384,7 +387,7 @@ static int build_from_dense(sslapb_handle *h, const double *mat, int32_t n_rows,
     }
     CK(cudaEventRecord(h->ev[2], h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    h->N = n_rows; h->M = n_cols; h->nnz = nnz; h->has_vals = want_vals;
+    h->N = n_rows; h->M = n_cols; h->nnz = nnz; h->has_vals = want_vals; h->hot_valid = false;
     return SSLAPB_OK;
 }
 
@@ -481,6 +484,25 @@ static int reserve_auction_state(sslapb_handle *h, SslapbAuctionParams &P)
     return SSLAPB_OK;
 }
 
+// Hot lists of the resident CSR (hot.cu): rest[N] | hthr[N] | N x 32 entries, one allocation; built once per resident problem.
+static int attach_hot_lists(sslapb_handle *h, SslapbAuctionParams &P, size_t *total_out, char **base_out)
+{
+    const size_t N = (size_t)h->N;
+    const size_t head = ((N * 16) + 511) & ~(size_t)511, total = head + N * 512;
+    CK(h->hotbuf.reserve(total));
+    char *hb = h->hotbuf.as<char>();
+    P.rest = reinterpret_cast<double *>(hb); P.hthr = reinterpret_cast<double *>(hb) + N;
+    SslapbHotEnt *hot = reinterpret_cast<SslapbHotEnt *>(hb + head);
+    P.hot = hot;
+    if (!h->hot_valid) {
+        CK(sslapb_launch_hot_build(P.rowptr, P.cols, P.vals, h->N, hot, const_cast<double *>(P.hthr), h->sms, h->stream));
+        h->hot_valid = true;
+    }
+    if (total_out) *total_out = total;
+    if (base_out) *base_out = hb;
+    return SSLAPB_OK;
+}
+
 static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize, float eps_start, int64_t max_iter,
                        int mem, int32_t *sol_out, sslapb_meta *meta)
 {
@@ -528,16 +550,13 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
     if (warm) CK(sslapb_launch_price_bounds(&P, h->stream));   // pruning bounds of the first phase from the caller's prices
     int grid = h->grid;
     if (h->max_ctas > 0 && h->max_ctas < grid) grid = h->max_ctas;
-    // ---- hot lists (hot.cu): the 32 largest entries of every row + the bound of the rest; not for the long-row instance
+    // ---- hot lists (hot.cu): the 32 largest entries of every row + the bound of the rest
     bool l2_window = false;
-    if (h->hot && !long_rows && N > 32) {
-        const size_t head = (((size_t)N * 16) + 511) & ~(size_t)511, total = head + (size_t)N * 512;
-        CK(h->hotbuf.reserve(total));
-        char *hb = h->hotbuf.as<char>();
-        P.rest = reinterpret_cast<double *>(hb); P.hthr = reinterpret_cast<double *>(hb) + N;
-        SslapbHotEnt *hot = reinterpret_cast<SslapbHotEnt *>(hb + head);
-        P.hot = hot;
-        CK(sslapb_launch_hot_build(P.rowptr, P.cols, P.vals, N, hot, const_cast<double *>(P.hthr), h->sms, h->stream));
+    if (h->hot && N > 32) {
+        size_t total = 0;
+        char *hb = nullptr;
+        rc = attach_hot_lists(h, P, &total, &hb);
+        if (rc) return rc;
         if (h->l2_persist && h->l2_persist_max > 0 && h->l2_window_max > 0) {   // loads from the hot lists (and rest[]) stay in L2 across the phase
             cudaStreamAttrValue av;
             memset(&av, 0, sizeof av);
@@ -899,6 +918,14 @@ extern "C" int sslapb_bid_sweep(sslapb_handle *h, const double *prices, const in
     // 768 / 1024 / 640 / 512, bit 6: untrimmed stage C); bit 7 = four rows per warp, 8 lanes per row (sweep4.cu)
     const bool pipelined = (merge & 8) != 0;
     const bool per_row = !pipelined && (merge & 128) == 0;
+    // bit 8: hot form — every bidder from its hot list when provably exact (bounds taken at the prices of this call), else
+    // the full-row sweep; what the persistent kernel's grid regime runs from the third eps-phase on
+    const bool hot_form = (merge & 256) != 0 && h->N > 32 && !streamed;
+    if (hot_form) {
+        rc = attach_hot_lists(h, P, nullptr, nullptr);
+        if (rc) return rc;
+        CK(sslapb_launch_hot_rest(&P, h->sms, h->stream));
+    }
     static const int sw2_threads[4] = {768, 1024, 640, 512};
     const int threads2 = sw2_threads[(merge >> 4) & 3];
     const int lean2 = (merge & 64) ? 0 : 1;                    // bit 6: the untrimmed stage C (A/B)
@@ -915,6 +942,7 @@ extern "C" int sslapb_bid_sweep(sslapb_handle *h, const double *prices, const in
         if (flush_l2) CK(cudaMemsetAsync(h->flush.p, it & 0xff, flush_bytes, h->stream));
         CK(cudaEventRecord(h->ev[3], h->stream));
         if (streamed) CK(sslapb_launch_bid_sweep_tma(&P, h->sweep_plan.as<int>(), eps, merge, h->sms, h->stream));
+        else if (hot_form) CK(sslapb_launch_bid_sweep_hot(&P, d_bidders, nb, eps, merge, h->sms, h->stream));
         else if (per_row) CK(sslapb_launch_bid_sweep(&P, d_bidders, nb, eps, merge, h->sms, h->stream));
         else if (pipelined) CK(sslapb_launch_bid_sweep2(&P, d_bidders, nb, eps, merge, threads2, lean2, h->sms, h->stream));
         else CK(sslapb_launch_bid_sweep4(&P, d_bidders, nb, eps, merge, h->sms, h->stream));

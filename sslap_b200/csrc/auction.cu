@@ -618,7 +618,6 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
     return nu;
 }
 
-#ifndef SSLAPB_LONG_ROWS
 // ----------------------------------------------------------------------------------------------------------------------
 // Hot-list forms of chain_rounds / multi_rounds (hot.cu), used in the eps-phases whose probing round found the hot lists
 // decisive.  Same round structure, same publications, same commits — only the sweep differs: 512 bytes and one record
@@ -785,8 +784,6 @@ __device__ __forceinline__ int multi_rounds_hot(const SslapbAuctionParams &P, do
     }
     return nu;
 }
-#endif
-
 // ---- long rows (more than one warp pass, e.g. dense inputs) in the single-bidder chain: the WHOLE CTA sweeps the row,
 // warp w taking the 32-chunk trips w, w+16, ...; the per-warp top-2 go through shared memory and warp 0 combines them,
 // commits and publishes the next bidder.  Two block barriers per round, independent of the row length up to 2048 entries
@@ -1062,9 +1059,6 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
     long long lst = 0;
     long long rw = 0, rs = 0;
     int fell = 0;                                              // hot mode: bids of this warp the hot list could not decide
-#ifdef SSLAPB_LONG_ROWS
-    hot = false;                                               // (the long-row instance keeps the full-row loops)
-#endif
     if (tid == 0) { s_bounds[0] = pmin; s_bounds[1] = spread; }
     if (warp == 0) {
         if (lane < nu) {
@@ -1082,8 +1076,15 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
     while (nu > SSLAPB_THREADS / 32 && !done) {
         for (int a = warp; a < nu; a += SSLAPB_THREADS / 32) {
             const long long st = s_start[a];
-            const SslapbBid b = row_bid_rec<32>(P.cols, P.vals, P.rec, st, st + s_deg[a], lane, eps, s_bounds[0],
-                                                __ldg(P.rowmax + s_list[a]) - s_bounds[1]);
+            SslapbBid b;
+            bool ok = false;
+            if (hot) {
+                SslapbHotRow unused;
+                ok = sweep_hot(P, sslapb_load_hot(P, s_list[a], true), eps, false, b, unused);
+                if (!ok) ++fell;
+            }
+            if (!ok) b = row_bid_rec<32>(P.cols, P.vals, P.rec, st, st + s_deg[a], lane, eps, s_bounds[0],
+                                         __ldg(P.rowmax + s_list[a]) - s_bounds[1]);
             if (lane == 0) s_bid[a] = b;
         }
         __syncthreads();
@@ -1101,22 +1102,16 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
         its = __shfl_sync(SSLAPB_FULL, s_its, 0);
     }
     // ---- 2..16 bidders: one warp per list position, distributed merge
-#ifndef SSLAPB_LONG_ROWS
     if (nu > 1 && !done && hot) nu = multi_rounds_hot(P, eps, s_bounds, nu, s_list, s_start, s_deg, its, max_iter, done, rw, li, lst, ldg, fell);
-    else
-#endif
-    if (nu > 1 && !done) nu = multi_rounds(P, eps, s_bounds, nu, s_list, s_start, s_deg, s_j, s_bidv, its, max_iter, done, rw, li, lst, ldg);
+    else if (nu > 1 && !done) nu = multi_rounds(P, eps, s_bounds, nu, s_list, s_start, s_deg, s_j, s_bidv, its, max_iter, done, rw, li, lst, ldg);
 
     unsigned long long tw1 = sslapb_globaltimer();
     // ---- single-bidder chain: warp 0 alone, no block barrier (after multi_rounds warp a holds position a in registers);
     // whenever the bidder's row is longer than one warp pass the whole CTA sweeps it (coop_chain_rounds)
     for (;;) {
         if (warp == 0) {
-#ifndef SSLAPB_LONG_ROWS
             if (nu == 1 && !done && hot) nu = chain_rounds_hot(P, eps, s_bounds, li, lst, ldg, its, max_iter, done, rs, fell);
-            else
-#endif
-            if (nu == 1 && !done) nu = chain_rounds(P, eps, li, lst, ldg, its, max_iter, done, rs);
+            else if (nu == 1 && !done) nu = chain_rounds(P, eps, li, lst, ldg, its, max_iter, done, rs);
             const bool longrow = nu == 1 && !done;             // chain_rounds stops in front of a long row
             if (lane == 0) {
                 s_row.st = lst; s_row.dg = ldg; s_row.me = li; s_row.state = longrow ? 0 : 1;
@@ -1773,6 +1768,82 @@ __global__ void __launch_bounds__(1024, 1) sslapb_bid_sweep_kernel(SslapbAuction
         a = an; st = stn; en = enn; rmax = rmaxn;
     }
     if (n2nd && lane == 0) atomicAdd((unsigned long long *)&P.ctrl->prune_second_pass, (unsigned long long)n2nd);
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Stand-alone bidding sweep in hot form: every bidder is decided from its hot list (512 B + one price gather per lane) when
+// that is provably exact, else by the full-row sweep of the kernel above — the same two-step the grid regime of the
+// persistent kernel runs from the third eps-phase on.  Results are bit-identical to the full-row kernels.
+// ----------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512, 2) sslapb_bid_sweep_hot_kernel(SslapbAuctionParams P, const int *__restrict__ bidders, int nb,
+                                                                     float eps_f, int merge)
+{
+    const int lane = threadIdx.x & 31;
+    const int wpc = blockDim.x >> 5;
+    const int gwarp = blockIdx.x * wpc + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * wpc;
+    const double eps = (double)eps_f;
+    const bool prune = (merge & 2) == 0;
+    const double pmin = sslapb_key2double(P.ctrl->pmin_key[0]);
+    double spread = sslapb_key2double(P.ctrl->pmax_key) - pmin;
+    if (!(spread < 1.7e308)) spread = __longlong_as_double(0x7ff0000000000000ll);
+    int n2nd = 0, nfell = 0;
+    merge &= 1;
+    for (int a = gwarp; a < nb; a += nwarps) {
+        const int i = bidders ? __ldg(bidders + a) : a;
+        const SslapbBid o = row_bid_hot(P.hot, P.rest, P.price, i, lane, eps);
+        int j = o.j;
+        double bid = o.bid;
+        if (j < 0) {                                           // the hot list cannot prove its answer: the whole row
+            ++nfell;
+            const long long st = __ldg(P.rowptr + i), en = __ldg(P.rowptr + i + 1);
+            const double thr = prune ? __ldg(P.rowmax + i) - spread : SSLAPB_NEG_INF;
+            if ((((en + 3) >> 2) - (st >> 2)) <= 32) {
+                const SslapbStreamChunk c = sslapb_stream_chunk(P.cols, P.vals, st, en, lane);
+                const SslapbBid f = row_bid_pruned(c, P.price, st, en, lane, eps, pmin, thr, n2nd);
+                j = f.j; bid = f.bid;
+                if (j < 0) row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid);
+            } else {
+                row_bid<32>(P.cols, P.vals, P.price, st, en, lane, eps, j, bid, pmin, thr);
+            }
+        }
+        if (lane == 0) {
+            P.bidj[a] = j;
+            P.bidv[a] = bid;
+            if (merge && j >= 0) atomicMax(P.bidkey + j, sslapb_ord64(bid));
+        }
+    }
+    if (lane == 0 && (n2nd | nfell)) {
+        if (n2nd) atomicAdd((unsigned long long *)&P.ctrl->prune_second_pass, (unsigned long long)n2nd);
+        atomicAdd((unsigned long long *)&P.ctrl->hot_grid[1], (unsigned long long)nfell);
+    }
+}
+
+// rest[i] = upper bound of a_ik - p_k over the entries outside person i's hot list, at the current prices (what every
+// eps-CS sweep of the persistent kernel leaves behind); stand-alone sweep only
+__global__ void __launch_bounds__(256) sslapb_hot_rest_kernel(SslapbAuctionParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    if (gwarp == 0 && lane == 0) P.ctrl->hot_grid[1] = 0;
+    for (int i = gwarp; i < P.N; i += nwarps) {
+        double vmax, choice, csum, rst;
+        row_ece<true>(P.cols, P.vals, P.price, __ldg(P.rowptr + i), __ldg(P.rowptr + i + 1), lane, -1, vmax, choice, csum, P.hthr[i], &rst);
+        if (lane == 0) P.rest[i] = rst;
+    }
+}
+
+extern "C" cudaError_t sslapb_launch_hot_rest(const SslapbAuctionParams *P, int sms, cudaStream_t stream)
+{
+    sslapb_hot_rest_kernel<<<sms * 8, 256, 0, stream>>>(*P);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t sslapb_launch_bid_sweep_hot(const SslapbAuctionParams *P, const int *bidders, int nb, float eps,
+                                                   int merge, int grid, cudaStream_t stream)
+{
+    sslapb_bid_sweep_hot_kernel<<<grid * 2, 512, 0, stream>>>(*P, bidders, nb, eps, merge);
+    return cudaGetLastError();
 }
 
 // Initial state of a solve (AuctionSolver.__init__, auction_.pyx:220-261).

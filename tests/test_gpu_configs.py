@@ -176,6 +176,42 @@ def test_warm_start_and_strict_mode(gpu, oracle_mod):
         h.set_option("strict", 0)
 
 
+def test_hot_lists_decide_bids_and_change_nothing(gpu, oracle_mod):
+    """Hot lists (csrc/hot.cu): the 32 largest entries of a row decide a bid only when that is provably exact.  The solve
+    must use them (from the third eps-phase on most bids are decided there, some are handed on to the full-row sweep),
+    must skip compaction in rounds without a hole, and sol / meta / float64 prices must equal the oracle's and the
+    hot-less run's, bit for bit — sparse float and int costs, wide rows (more than one warp pass) and a dense matrix."""
+    sslap_b200, nat, h = gpu
+    cases = [(4000, 0.02, "float", 11), (3000, 0.03, "int", 12), (1500, 0.2, "float", 13), (20000, 0.003, "float", 14)]
+    for (n, d, mode, seed) in cases:
+        loc, val = make_problem(n, d, mode, seed=seed)
+        want = oracle_mod.auction_solve(loc=loc, val=val, problem="min", return_prices=True)
+        got = sslap_b200.auction_solve(loc=loc, val=val, size=(n, n), problem="min", cardinality_check=False, _raw_meta=True,
+                                       return_prices=True)
+        raw = got["raw"]
+        assert raw.hot_grid_bids > 0 and raw.hot_tail_rounds > 0, (n, raw.hot_grid_bids, raw.hot_tail_rounds)
+        assert raw.hot_grid_fallbacks > 0                                    # the first phase has no bounds yet: all handed on
+        assert 0 < raw.rounds_nohole <= raw.rounds_grid
+        h.set_option("hot", 0)
+        try:
+            off = sslap_b200.auction_solve(loc=loc, val=val, size=(n, n), problem="min", cardinality_check=False,
+                                           _raw_meta=True, return_prices=True)
+        finally:
+            h.set_option("hot", 1)
+        assert off["raw"].hot_grid_bids == 0 and off["raw"].hot_tail_rounds == 0
+        for r in (got, off):
+            assert np.array_equal(r["sol"], want["sol"]), (n, mode)
+            assert_meta_equal(r["meta"], want["meta"])
+            assert np.array_equal(r["prices"], want["prices"]), (n, mode)
+    rng = np.random.default_rng(5)
+    mat = rng.uniform(0, 100, (1300, 1300))                                  # dense: rows of 1300 entries, the long-row instance
+    want = oracle_mod.auction_solve(mat=mat, problem="max", return_prices=True)
+    got = sslap_b200.auction_solve(mat=mat, problem="max", _raw_meta=True, return_prices=True)
+    assert got["raw"].hot_tail_rounds > 0
+    assert np.array_equal(got["sol"], want["sol"]) and np.array_equal(got["prices"], want["prices"])
+    assert_meta_equal(got["meta"], want["meta"])
+
+
 @pytest.mark.parametrize("k_ranks", [2, 4, 8])
 def test_row_sharded_solve_with_virtual_ranks_on_one_gpu(gpu, oracle_mod, k_ranks):
     """SURVEY.md §8(e) with K virtual ranks on ONE GPU: K handles, K concurrent persistent kernels (grids of sms/K CTAs so

@@ -13,6 +13,7 @@ static void stats_bid(const void *s, int nb, int i, double vbest, double wi, int
 static const int HS[NH] = {8, 16, 24, 32};
 static double *g_hmin[NH];
 static double g_pmin;
+static long long g_nb_hist[40];
 static int g_prev_nb = -1; static long long g_grid_rounds, g_grid_same, g_hist_same[8], g_hist_all[8];
 static long long g_ph_h[64][NH];
 static double *g_restR; static long long g_ph_tail[64], g_ph_pass[64], g_ph_passR[64], g_ph_chain[64], g_ph_chain_pass[64];
@@ -81,6 +82,7 @@ static void stats_bid(const void *sv, int nb, int i, double vbest, double wi, in
         }
     }
     if (i == s->unassigned[0]) {                     /* first bid of a round */
+        if (nb <= 32) ++g_nb_hist[nb];
         if (g_prev_nb > 32) {
             int b = g_prev_nb <= 128 ? 0 : g_prev_nb <= 512 ? 1 : g_prev_nb <= 2048 ? 2 : g_prev_nb <= 8192 ? 3 : 4;
             ++g_grid_rounds; ++g_hist_all[b];
@@ -103,6 +105,7 @@ static void stats_bid(const void *sv, int nb, int i, double vbest, double wi, in
 
 void stats_report(void)
 {
+    printf("rounds by frontier size:"); for (int k = 1; k <= 32; ++k) printf(" %d:%lld", k, g_nb_hist[k]); printf("\n");
     printf("grid rounds %lld, of which the frontier size did not change (no hole): %lld\n", g_grid_rounds, g_grid_same);
     for (int b = 0; b < 5; ++b) printf("  frontier bucket %d: rounds %lld no-hole %lld\n", b, g_hist_all[b], g_hist_same[b]);
     for (int p = 1; p <= g_phase; ++p) printf("phase %2d: tail bids %8lld  pass(static32) %.4f  pass(with refresh) %.4f   chain bids %8lld pass(refresh) %.4f\n", p, g_ph_tail[p], (double)g_ph_pass[p] / (g_ph_tail[p] ? g_ph_tail[p] : 1), (double)g_ph_passR[p] / (g_ph_tail[p] ? g_ph_tail[p] : 1), g_ph_chain[p], (double)g_ph_chain_pass[p] / (g_ph_chain[p] ? g_ph_chain[p] : 1));

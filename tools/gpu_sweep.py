@@ -20,7 +20,8 @@ sslap_b200.auction_solve(loc=loc, val=val, size=(n, n), cardinality_check=False)
 by = 12 * val.size + 36 * n
 variants = [("4 rows/warp, 8 lanes/row", 1 | 128), ("4 rows/warp, pruning off", 3 | 128),
             ("per-row kernel (default)", 1), ("per-row kernel, pruning off", 3),
-            ("pipelined per-row 768 thr", 1 | 8), ("pipelined per-row 1024 thr", 1 | 8 | 16), ("TMA ring", 1 | 4)]
+            ("pipelined per-row 768 thr", 1 | 8), ("pipelined per-row 1024 thr", 1 | 8 | 16), ("TMA ring", 1 | 4),
+            ("hot form (hot lists + exact fallback)", 1 | 256)]
 for rep in range(2):
     for name, merge in variants:
         ms = C.c_float(0)
