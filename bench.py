@@ -138,11 +138,11 @@ def reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def ncu_traffic_bytes():
+def ncu_traffic_bytes(names=("r2_bid_sweep_hot_raw.csv",)):
     """DRAM bytes of ONE launch of the roofline kernel on this workload, from the committed ncu capture (never measured
     under the profiler inside a bench run); None when the capture is missing."""
     import csv
-    for name in ("r2_bid_sweep_full_raw.csv", "r1_bid_sweep_full_raw_final.csv"):
+    for name in names:
         path = os.path.join(ROOT, "profiles", name)
         try:
             with open(path, newline="") as f:
@@ -242,7 +242,10 @@ def main():
     its, obj = int(meta.its), objective(loc, val, sol)
     assert sorted(sol.tolist()) == list(range(N_ROWS)) and meta.soln_found == 1, "bench solve did not produce a perfect optimal matching"
     rounds_sharded, row_range = int(meta.rounds_sharded), (int(meta.row_lo), int(meta.row_hi))
-    launches_per_step = 4 + (1 if world > 1 else 0)   # coo_ingest, rowmax, auction_init, persistent kernel (+ row_split)
+    launches_per_step = 5 + (1 if world > 1 else 0)   # coo_ingest, rowmax, hot_build, auction_init, persistent kernel (+ row_split)
+    hot_stats = {"grid_bids": int(meta.hot_grid_bids), "grid_fallbacks": int(meta.hot_grid_fallbacks),
+                 "tail_rounds": int(meta.hot_tail_rounds), "tail_fallbacks": int(meta.hot_tail_fallbacks),
+                 "grid_rounds_without_compaction": int(meta.rounds_nohole)}
 
     # ---------------- leg 2: end to end through the public API, host buffers ----------------
     p_loc = L.sslapb_host_alloc(loc.nbytes)
@@ -270,13 +273,20 @@ def main():
     gpu_launches = launches_per_step * args.steps
 
     # ---------------- roofline of the dominant-bandwidth kernel: the full-frontier bidding sweep ----------------
-    avg = C.c_float(0)
-    rc = L.sslapb_bid_sweep(h.ptr, None, None, N_ROWS, float(np.float32(1.0 / N_ROWS)), 1, 20, 1, None, None, C.byref(avg))
+    # The product's sweep = hot form (merge bit 8): every bidder from its hot list when provably exact, else the full row;
+    # the streaming-only kernel (every row read in full, round 1's roofline kernel) is timed beside it.
+    avg, avg_stream = C.c_float(0), C.c_float(0)
+    eps_sw = float(np.float32(1.0 / N_ROWS))
+    rc = L.sslapb_bid_sweep(h.ptr, None, None, N_ROWS, eps_sw, 1 | 256, 20, 1, None, None, C.byref(avg))
+    assert rc == 0
+    rc = L.sslapb_bid_sweep(h.ptr, None, None, N_ROWS, eps_sw, 1, 20, 1, None, None, C.byref(avg_stream))
     assert rc == 0
     sweep_bytes = 12 * nnz + 36 * N_ROWS               # SURVEY.md §8(d) / DESIGN.md §4.2: 12 B per CSR entry + 36 B per bidder
     peak, peak_src = measured_peaks()
     achieved = sweep_bytes / (avg.value * 1e-3) / 1e9
+    achieved_stream = sweep_bytes / (avg_stream.value * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic_bytes()
+    traffic_stream, traffic_stream_src = ncu_traffic_bytes(("r2_bid_sweep_stream_raw.csv", "r1_bid_sweep_full_raw_final.csv"))
 
     # ---------------- configs[4]: 4096 independent 512 x 512 problems, dealt out to the ranks ----------------
     c5 = None
@@ -335,18 +345,24 @@ def main():
             "solve_s": ms_step * 1e-3,
             "device_ms": {"csr_build": float(np.mean(setup_ms)), "auction_kernel": float(np.mean(solve_ms)),
                           "rounds": {"grid": int(meta.rounds_grid), "warp": int(meta.rounds_warp), "chain": int(meta.rounds_solo)},
-                          "sections_ms": [round(float(x), 3) for x in meta.prof_ms]},
+                          "sections_ms": [round(float(x), 3) for x in meta.prof_ms], "hot_lists": hot_stats},
             "e2e": {"value": nnz / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(loc.nbytes + val.nbytes) * world,
                     "d2h_bytes_per_step": int(sol.nbytes + 8 * N_ROWS + 512) * world, "host_memory": "pinned"},
             "e2e_pageable": {"value": nnz / (e2e_pageable_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_pageable_ms,
                              "host_memory": "pageable numpy arrays, default handle: the literal drop-in call"},
             "gpu_launches": gpu_launches,
-            "roofline": {"kernel": "sslapb_bid_sweep_kernel (full frontier, N bidders, merge atomics on)", "bound": "hbm",
+            "roofline": {"kernel": "sslapb_bid_sweep_hot_kernel (full frontier, N bidders, merge atomics on): the bidding step as the solver "
+                                   "runs it — hot list first (512 B per row), full CSR row when that is not provably exact", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": f"{traffic_src} (ncu --set full of this launch: "
                          "dram__bytes_read.sum + dram__bytes_write.sum)" if traffic_src else None,
                          "bytes_per_launch": sweep_bytes, "avg_launch_us": avg.value * 1e3,
+                         "bytes_note": "algorithmic bytes = 12 B x entries of the bidders' rows + 36 B x bidders (SURVEY.md 8d); the hot form "
+                                       "reads fewer (see traffic): it skips row entries it can prove irrelevant",
+                         "streaming_only": {"kernel": "sslapb_bid_sweep_kernel: every row read in full (round 1's roofline kernel)",
+                                            "achieved": achieved_stream, "frac": achieved_stream / peak, "avg_launch_us": avg_stream.value * 1e3,
+                                            "traffic": traffic_stream, "traffic_source": traffic_stream_src},
                          "insitu": {"what": "bidding step of the full-frontier rounds inside the persistent kernel (512-thread CTAs, "
                                             "globaltimer, incl. the grid barrier that ends the step); at N>1 each rank sweeps 1/N of the rows",
                                     "avg_us": float(np.mean(insitu_us)), "rounds_per_solve": int(meta.sweep_insitu_n),

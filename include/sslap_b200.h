@@ -102,7 +102,7 @@ int    sslapb_abi_version(void);
    device-resident loop; A/B runs; default 0),
    "batch_v1" (1: round 1's batch kernel — a whole warp sweeps one bidder at a time — instead of the sub-warp kernel; A/B runs),
    "hot" (0: never decide bids from the hot lists — A/B runs; default 1),
-   "l2_persist" (0: no persisting L2 access-policy window over the hot lists during a solve — A/B runs; default 1),
+   "l2_persist" (1: persisting L2 access-policy window over the hot lists during a solve — A/B runs; measured no gain; default 0),
    "coop" (row-sharded solves only; 0: launch the persistent kernel without the cooperative attribute so that several of them
    can run side by side on ONE GPU — the driver runs one cooperative kernel at a time; only for the virtual-rank test, default 1),
    "strict" (1: strict-optimality stop rule — eps-CS is tested with eps = 1/(N+1) and zero tolerance and the eps schedule runs

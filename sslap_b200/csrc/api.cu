@@ -121,7 +121,8 @@ struct sslapb_handle {
     int strict = 0;                // strict-optimality stop rule (see the header)
     int coop = 1;                  // 0: launch the row-sharded persistent kernel without the cooperative attribute (virtual ranks)
     int hot = 1;                   // hot lists (hot.cu): 0 = off (A/B runs)
-    int l2_persist = 1;            // 1: L2 access-policy window (persisting) over the hot lists during a solve; 0 = off (A/B runs)
+    int l2_persist = 0;            // 1: L2 access-policy window (persisting) over the hot lists during a solve (measured: no gain at C3,
+                                   // 233.0 vs 233.1 ms — the lists stay in L2 on their own; kept for A/B runs)
     size_t l2_persist_max = 0;     // cudaDevAttrMaxPersistingL2CacheSize
     int l2_window_max = 0;         // cudaDevAttrMaxAccessPolicyWindowSize
     // warm start: prices for the next solve (sslapb_set_prices)
@@ -549,6 +550,9 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
     CK(cudaMemcpyAsync(P.ctrl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
     if (warm) CK(sslapb_launch_price_bounds(&P, h->stream));   // pruning bounds of the first phase from the caller's prices
     int grid = h->grid;
+    // small problems: a grid barrier among 148 CTAs costs more than the few rows the extra CTAs would sweep (measured, dense
+    // N = 10 / 32 / 100: 1 / 2-4 / 4-16 CTAs are the fastest, tools/gpu_small.py); one CTA per 8 persons, at least one
+    if (!sharded && (N + 7) / 8 < grid) grid = (N + 7) / 8;
     if (h->max_ctas > 0 && h->max_ctas < grid) grid = h->max_ctas;
     // ---- hot lists (hot.cu): the 32 largest entries of every row + the bound of the rest
     bool l2_window = false;
