@@ -2,7 +2,7 @@
 the validity checks that script computes but never asserts: complete assignment, only admissible entries used, and the
 objective compared with scipy's optimum.  No plots (matplotlib is not in the image): prints one table per sweep.
 
-    python tools/benchmarking.py [--max-size 3000] [--reference]
+    python tools/benchmarking.py [--max-size 10000] [--reference]
 
 Inputs follow the reference: seeded dense matrix (np.random.seed(1), uniform(0,100) or randint(1,100)), sparsified with
 np.random.seed(2) at the requested density, every row/column kept feasible, invalid entries = -1, problem='max',
@@ -74,7 +74,7 @@ def timeit(fn, reps=3):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--max-size", type=int, default=3000)
+    ap.add_argument("--max-size", type=int, default=10000)
     ap.add_argument("--reference", action="store_true", help="also time the unmodified reference (oracle/_ref) when present")
     args = ap.parse_args()
     import sslap_b200
