@@ -218,7 +218,7 @@ struct SslapbHotRow { int col, idx; double a, rest; };
 __device__ __forceinline__ SslapbHotRow sslapb_load_hot(const SslapbAuctionParams &P, int person, bool active)
 {
     SslapbHotRow h;
-    h.col = -1; h.idx = -1; h.a = SSLAPB_NEG_INF; h.rest = __longlong_as_double(0x7ff0000000000000ll);
+    h.col = 0; h.idx = -1; h.a = SSLAPB_NEG_INF; h.rest = __longlong_as_double(0x7ff0000000000000ll);
     if (active) {
         const int4 q = __ldg(reinterpret_cast<const int4 *>(P.hot) + (long long)person * 32 + (threadIdx.x & 31));
         h.col = q.x; h.idx = q.y; h.a = __hiloint2double(q.w, q.z);
@@ -226,40 +226,49 @@ __device__ __forceinline__ SslapbHotRow sslapb_load_hot(const SslapbAuctionParam
     }
     return h;
 }
-__device__ __forceinline__ bool sweep_hot(const SslapbAuctionParams &P, const SslapbHotRow &cur, double eps, bool want_next,
-                                          SslapbBid &B, SslapbHotRow &nxt)
+// NEXT: request the hot row of the object's current owner (unconditionally — index clamped to 0 when there is none; the
+// callers never use `nxt` then) as soon as the winner is known.  `nxt` is written only when the function returns true.
+template <bool NEXT>
+__device__ __forceinline__ bool sweep_hot(const SslapbAuctionParams &P, const SslapbHotRow &cur, double eps, SslapbBid &B,
+                                          SslapbHotRow &nxt)
 {
     const int lane = threadIdx.x & 31;
-    SslapbRec256 q;
-    q.start = 0ull; q.owner_deg = 0xffffffffull; q.price_bits = 0ull;
-    const bool m = cur.col >= 0;
-    if (m) q = sslapb_ld_rec256(P.rec + cur.col);
-    const double v = m ? cur.a - __longlong_as_double((long long)q.price_bits) : SSLAPB_NEG_INF;
-    const bool has = v > SSLAPB_NEG_INF;
-    const unsigned long long bk = has ? sslapb_key_of(v) : 0ull;
+    // padding entries carry (column 0, a = -inf): gathered like the others, their value -inf - p = -inf never wins
+    const SslapbRec256 q = sslapb_ld_rec256(P.rec + cur.col);
+    // (measured and dropped: every lane prefetching its candidate's owner's hot row into L1 ahead of the reduction — 128
+    // prefetches per round cost more than the L2 round trip they hide: C3 233.7 -> 248.5 ms)
+    const double v = (cur.a - __longlong_as_double((long long)q.price_bits)) + 0.0;   // + 0.0 folds -0.0 into +0.0
+    const unsigned long long bk = sslapb_ord64(v);             // -inf (padding, objects priced +inf) -> SSLAPB_KEY_NEG_INF
     const unsigned bh = (unsigned)(bk >> 32), bl = (unsigned)bk;
     const unsigned khi = __reduce_max_sync(SSLAPB_FULL, bh);
-    const unsigned hm = __ballot_sync(SSLAPB_FULL, (bh == khi) & has);
+    if (khi <= (unsigned)(SSLAPB_KEY_NEG_INF >> 32)) return false;     // every candidate at -inf: the exact generic sweep decides
+    const unsigned hm = __ballot_sync(SSLAPB_FULL, bh == khi);
     bool iswin;
     unsigned own;
-    if (__popc(hm) <= 1) {
+    if ((hm & (hm - 1u)) == 0u) {                              // one lane holds the maximal high word: it is the winner
         own = hm;
-        iswin = (hm >> lane) & 1u;
+        iswin = bh == khi;
     } else {
         const unsigned klo = __reduce_max_sync(SSLAPB_FULL, bh == khi ? bl : 0u);
-        const bool top = (bh == khi) & (bl == klo) & has;
+        const bool top = (bh == khi) & (bl == klo);
         const int widx = __reduce_max_sync(SSLAPB_FULL, top ? cur.idx : -1);   // equal values: the later row entry wins (:351)
         iswin = top & (cur.idx == widx);
         own = __ballot_sync(SSLAPB_FULL, iswin);
     }
-    nxt = cur;
-    if (own == 0u) return false;
-    const int src = __ffs(own) - 1;
+    int src;                                                   // the one lane of `own`
+    asm("bfind.u32 %0, %1;" : "=r"(src) : "r"(own));
     const unsigned long long wo = __shfl_sync(SSLAPB_FULL, q.owner_deg, src);
     B.pstart = (long long)__shfl_sync(SSLAPB_FULL, q.start, src);
     B.powner = (int)(unsigned)wo;
     B.pdeg = (int)(wo >> 32);
-    nxt = sslapb_load_hot(P, B.powner, want_next && B.powner >= 0);
+    SslapbHotRow nx;
+    nx.col = 0; nx.idx = -1; nx.a = SSLAPB_NEG_INF; nx.rest = SSLAPB_NEG_INF;
+    if (NEXT) {
+        const unsigned who = B.powner >= 0 ? (unsigned)B.powner : 0u;
+        const int4 h4 = __ldg(reinterpret_cast<const int4 *>(reinterpret_cast<const char *>(P.hot) + ((unsigned long long)who << 9)) + lane);
+        nx.col = h4.x; nx.idx = h4.y; nx.a = __hiloint2double(h4.w, h4.z);
+        nx.rest = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(P.rest) + ((unsigned long long)who << 3));
+    }
     // ---- everything below overlaps the load above
     const unsigned long long cand = iswin ? 0ull : bk;         // one candidate per lane: second best = best of the other lanes
     const unsigned chh = (unsigned)(cand >> 32), chl = (unsigned)cand;
@@ -270,17 +279,22 @@ __device__ __forceinline__ bool sweep_hot(const SslapbAuctionParams &P, const Ss
     B.j = __shfl_sync(SSLAPB_FULL, cur.col, src);
     const double wi = skey > SSLAPB_KEY_NEG_INF ? sslapb_key2double(skey) : SSLAPB_NEG_INF;   // :344
     B.bid = (bc - wi) + eps;                                   // :360
-    return (wi > cur.rest) || (cur.rest == SSLAPB_NEG_INF);
+    if (!((wi > cur.rest) || (cur.rest == SSLAPB_NEG_INF))) return false;
+    nxt = nx;
+    return true;
 }
 
-// One bidder of the few-bidder / chain regimes in hot form: decide from the hot list, otherwise sweep the full row with the
-// exact generic sweep (bound-pruned when the row is longer than one warp pass) and request the next occupant's hot row.
+// One bidder of the few-bidder rounds in hot form: decide from the hot list, otherwise sweep the full row with the exact
+// generic sweep (bound-pruned when the row is longer than one warp pass) and request the next occupant's hot row.
+// (Measured: moving this fallback out of line, with the publication written by either path and read back after the
+// barrier, made these rounds slower — 1.20 against 1.06 us — although it removed 50 instructions from the loop; the
+// single-warp chain, by contrast, gained 11 % from exactly that treatment, see chain_rounds_hot.)
 // `fell` counts the bids the hot list could not decide.  Returns false for a row without any entry.
 __device__ __forceinline__ bool hot_bid(const SslapbAuctionParams &P, const SslapbHotRow &cur, int me, long long st, int dg,
                                         double eps, const double *s_bounds, bool want_next, SslapbBid &B, SslapbHotRow &nxt,
                                         int &fell)
 {
-    if (sweep_hot(P, cur, eps, want_next, B, nxt)) return true;
+    if (sweep_hot<true>(P, cur, eps, B, nxt)) return true;
     ++fell;
     const bool single = (((st + dg + 3) >> 2) - (st >> 2)) <= 32;
     B = row_bid_rec<32>(P.cols, P.vals, P.rec, st, st + dg, threadIdx.x & 31, eps, s_bounds[0],
@@ -625,31 +639,48 @@ __device__ __forceinline__ int multi_rounds(const SslapbAuctionParams &P, double
 // ----------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int chain_rounds_hot(const SslapbAuctionParams &P, double eps, const double *s_bounds, int &li,
                                                 long long &lst, int &ldg, long long &its, long long max_iter, int &done,
-                                                long long &rounds, int &fell)
+                                                long long &rounds, int &fell, bool &hot)
 {
     const int lane = threadIdx.x & 31;
     li = __shfl_sync(SSLAPB_FULL, li, 0); lst = __shfl_sync(SSLAPB_FULL, lst, 0); ldg = __shfl_sync(SSLAPB_FULL, ldg, 0);
     int nu = 1;
-    SslapbHotRow cur = sslapb_load_hot(P, li, true);
-    while (nu == 1 && !done) {
-        SslapbBid B;
-        SslapbHotRow nxt;
-        if (!sweep_hot(P, cur, eps, its + 1 < max_iter, B, nxt)) {
-            ++fell;
-            // undecided: rows of more than one warp pass are left to the whole CTA (coop_chain_rounds), the others are
-            // swept exactly (every entry gathered) right here
-            if ((((lst + ldg + 3) >> 2) - (lst >> 2)) > 32) break;
-            B = row_bid_rec<32>(P.cols, P.vals, P.rec, lst, lst + ldg, lane, eps);
-            if (B.j < 0) { done = 4; break; }
-            nxt = sslapb_load_hot(P, B.powner, B.powner >= 0);
+    const long long rounds0 = rounds;
+    int undecided_here = 0;
+    // One warp issues one instruction at a time and waits out every dependent latency, so a round costs what its
+    // instruction count costs (~4.4 cycles each, measured: tools/gpu_tailprobe.py) — the loop of the decided rounds is
+    // kept free of the fallback's code and of the register moves that merging two paths would put on the common one.
+    for (;;) {
+        SslapbHotRow cur = sslapb_load_hot(P, li, true);
+        bool undecided = false;
+        while (!done) {
+            SslapbBid B;
+            SslapbHotRow nxt;
+            if (!sweep_hot<true>(P, cur, eps, B, nxt)) { undecided = true; break; }
+            if (lane == 0) commit_win(P, li, lst, ldg, B);     // the only bidder wins (:379-385, :394-427)
+            __syncwarp();
+            ++its; ++rounds;
+            if (its >= max_iter) done = 3;
+            if (B.powner < 0) { nu = 0; li = -1; break; }      // nobody evicted: the frontier is empty
+            li = B.powner; lst = B.pstart; ldg = B.pdeg;       // the evicted owner is the next (and only) bidder
+            cur = nxt;
         }
-        if (lane == 0) commit_win(P, li, lst, ldg, B);         // the only bidder wins (:379-385, :394-427)
+        if (!undecided) break;
+        // ---- the hot list could not decide this bid (rare): rows of more than one warp pass are left to the whole CTA
+        // (coop_chain_rounds), the others are swept exactly (every entry gathered) right here
+        ++fell; ++undecided_here;
+        // a chain the hot lists keep failing on (price wars over objects priced +inf: every candidate at -inf) goes back to
+        // the full-row loop for the rest of the phase
+        if (undecided_here >= 32 && 2 * (long long)undecided_here > rounds - rounds0) { hot = false; break; }
+        if ((((lst + ldg + 3) >> 2) - (lst >> 2)) > 32) break;
+        const SslapbBid B = row_bid_rec<32>(P.cols, P.vals, P.rec, lst, lst + ldg, lane, eps);
+        if (B.j < 0) { done = 4; break; }
+        if (lane == 0) commit_win(P, li, lst, ldg, B);
         __syncwarp();
         ++its; ++rounds;
         if (its >= max_iter) done = 3;
-        if (B.powner < 0) { nu = 0; li = -1; break; }          // nobody evicted: the frontier is empty
-        li = B.powner; lst = B.pstart; ldg = B.pdeg;           // the evicted owner is the next (and only) bidder
-        cur = nxt;
+        if (B.powner < 0) { nu = 0; li = -1; break; }
+        li = B.powner; lst = B.pstart; ldg = B.pdeg;
+        if (done) break;
     }
     return nu;
 }
@@ -1080,7 +1111,7 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
             bool ok = false;
             if (hot) {
                 SslapbHotRow unused;
-                ok = sweep_hot(P, sslapb_load_hot(P, s_list[a], true), eps, false, b, unused);
+                ok = sweep_hot<false>(P, sslapb_load_hot(P, s_list[a], true), eps, b, unused);
                 if (!ok) ++fell;
             }
             if (!ok) b = row_bid_rec<32>(P.cols, P.vals, P.rec, st, st + s_deg[a], lane, eps, s_bounds[0],
@@ -1110,7 +1141,7 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
     // whenever the bidder's row is longer than one warp pass the whole CTA sweeps it (coop_chain_rounds)
     for (;;) {
         if (warp == 0) {
-            if (nu == 1 && !done && hot) nu = chain_rounds_hot(P, eps, s_bounds, li, lst, ldg, its, max_iter, done, rs, fell);
+            if (nu == 1 && !done && hot) nu = chain_rounds_hot(P, eps, s_bounds, li, lst, ldg, its, max_iter, done, rs, fell, hot);
             else if (nu == 1 && !done) nu = chain_rounds(P, eps, li, lst, ldg, its, max_iter, done, rs);
             const bool longrow = nu == 1 && !done;             // chain_rounds stops in front of a long row
             if (lane == 0) {

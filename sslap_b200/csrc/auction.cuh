@@ -48,7 +48,7 @@ struct SslapbCtrl {
 
 // One hot-list entry (hot.cu): 32 per person, 512 bytes per row, lane t of a warp reads entry t.
 struct __align__(16) SslapbHotEnt {
-    int col;                  // object, -1 = padding
+    int col;                  // object; padding entries: column 0 with a = -inf, idx = -1
     int idx;                  // index of the entry inside its CSR row (tie rule: the LAST maximal entry wins, auction_.pyx:351)
     double a;                 // value (sign-folded)
 };

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) sslapb_hot_build_kernel(const long long *
         const long long st = __ldg(rowptr + i);
         const int deg = (int)(__ldg(rowptr + i + 1) - st);
         SslapbHotEnt pad;
-        pad.col = -1; pad.idx = -1; pad.a = SSLAPB_NEG_INF;
+        pad.col = 0; pad.idx = -1; pad.a = SSLAPB_NEG_INF;         // gathered like a real entry: -inf - p = -inf never wins
         if (deg <= 32) {
             SslapbHotEnt e = pad;
             if (lane < deg) { e.col = __ldg(cols + st + lane); e.idx = lane; e.a = __ldg(vals + st + lane); }

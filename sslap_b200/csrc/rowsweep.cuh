@@ -317,8 +317,7 @@ __device__ __forceinline__ SslapbBid row_bid_hot(const SslapbHotEnt *__restrict_
     const int4 q = __ldg(reinterpret_cast<const int4 *>(hot) + (long long)person * 32 + lane);
     const double rest = rest_arr[person];
     const double a = __hiloint2double(q.w, q.z);
-    double v = SSLAPB_NEG_INF;
-    if (q.x >= 0) v = a - price[q.x];
+    const double v = a - price[q.x];                           // padding: column 0, a = -inf -> v = -inf
     const bool has = v > SSLAPB_NEG_INF;                       // real -inf candidates: left to the generic sweep
     const unsigned long long bk = has ? sslapb_key_of(v) : 0ull;
     const unsigned bh = (unsigned)(bk >> 32), bl = (unsigned)bk;

@@ -209,8 +209,19 @@ def test_reference_benchmarking_sweeps_at_reduced_size(gpu):
     for n in (10, 32, 100, 316, 562):
         for mode in ("float", "int"):
             run(bm.make_matrix(n, 1.0, mode), mode)
-    for dens in (0.01, 0.05, 0.2, 0.5):
+    for dens in (0.05, 0.2, 0.5):
         run(bm.make_matrix(500, dens, "float"), "float")
+    run(bm.make_matrix(1000, 0.01, "float"), "float")
+    # the same generator at N = 500, 1 % (rows of ~5 entries, several with one): single-choice bidders price objects at +inf
+    # and the auction runs into max_iter — in the reference too.  The GPU must stop on the very same state.
+    from oracle import oracle
+    mat = bm.make_matrix(500, 0.01, "float")
+    want = oracle.auction_solve(mat=mat, problem="max")
+    got = sslap_b200.auction_solve(mat, problem="max")
+    assert want["meta"]["its"] == 1000000 and want["meta"]["soln_found"] == 0
+    assert np.array_equal(got["sol"], want["sol"])
+    for k in ("its", "nreductions", "soln_found", "n_assigned", "eCE"):
+        assert got["meta"][k] == want["meta"][k], k
     if ref is not None:
         mat = bm.make_matrix(1000, 1.0, "float")
         sslap_b200.auction_solve(mat, problem="max")

@@ -27,6 +27,8 @@ def run(tag, n, d, reps=2, **kw):
 if which in ("c2", "both"):
     run("C2", 10000, 0.01)
     h.set_option("hot", 0); run("C2 hot off", 10000, 0.01, reps=1); h.set_option("hot", 1)
+if which == "c3only":
+    run("C3", 100000, 0.001, reps=3)
 if which in ("c3", "both"):
     loc, val = run("C3", 100000, 0.001)
     h.set_option("hot", 0); run("C3 hot off", 100000, 0.001, reps=1); h.set_option("hot", 1)
