@@ -652,6 +652,7 @@ __device__ __forceinline__ int chain_rounds_hot(const SslapbAuctionParams &P, do
     for (;;) {
         SslapbHotRow cur = sslapb_load_hot(P, li, true);
         bool undecided = false;
+#pragma unroll 2
         while (!done) {
             SslapbBid B;
             SslapbHotRow nxt;
