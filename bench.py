@@ -147,12 +147,13 @@ def ncu_traffic_bytes(names=("r2_bid_sweep_hot_raw.csv",)):
         try:
             with open(path, newline="") as f:
                 rows = list(csv.reader(f))
-            hdr, units, vals = rows[0], rows[1], rows[2]
+            hdr, units = rows[0], rows[1]
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             tot = 0.0
-            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                i = hdr.index(key)
-                tot += float(vals[i].replace(",", "")) * scale[units[i]]
+            for vals in rows[2:]:                                   # one row per kernel of the measured launch (the hot form is a pair)
+                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    i = hdr.index(key)
+                    tot += float(vals[i].replace(",", "")) * scale[units[i]]
             return int(tot), "profiles/" + name
         except Exception:
             continue
@@ -275,11 +276,15 @@ def main():
     # ---------------- roofline of the dominant-bandwidth kernel: the full-frontier bidding sweep ----------------
     # The product's sweep = hot form (merge bit 8): every bidder from its hot list when provably exact, else the full row;
     # the streaming-only kernel (every row read in full, round 1's roofline kernel) is timed beside it.
-    avg, avg_stream = C.c_float(0), C.c_float(0)
+    avg, avg_stream, avg_clean = C.c_float(0), C.c_float(0), C.c_float(0)
     eps_sw = float(np.float32(1.0 / N_ROWS))
+    for variant in (1 | 256, 1):                                            # untimed first launches (lazy module load)
+        assert L.sslapb_bid_sweep(h.ptr, None, None, N_ROWS, eps_sw, variant, 3, 1, None, None, C.byref(avg)) == 0
     rc = L.sslapb_bid_sweep(h.ptr, None, None, N_ROWS, eps_sw, 1 | 256, 20, 1, None, None, C.byref(avg))
     assert rc == 0
     rc = L.sslapb_bid_sweep(h.ptr, None, None, N_ROWS, eps_sw, 1, 20, 1, None, None, C.byref(avg_stream))
+    assert rc == 0
+    rc = L.sslapb_bid_sweep(h.ptr, None, None, N_ROWS, eps_sw, 1 | 256, 20, 2, None, None, C.byref(avg_clean))
     assert rc == 0
     sweep_bytes = 12 * nnz + 36 * N_ROWS               # SURVEY.md §8(d) / DESIGN.md §4.2: 12 B per CSR entry + 36 B per bidder
     peak, peak_src = measured_peaks()
@@ -352,14 +357,19 @@ def main():
             "e2e_pageable": {"value": nnz / (e2e_pageable_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_pageable_ms,
                              "host_memory": "pageable numpy arrays, default handle: the literal drop-in call"},
             "gpu_launches": gpu_launches,
-            "roofline": {"kernel": "sslapb_bid_sweep_hot_kernel (full frontier, N bidders, merge atomics on): the bidding step as the solver "
-                                   "runs it — hot list first (512 B per row), full CSR row when that is not provably exact", "bound": "hbm",
+            "roofline": {"kernel": "sslapb_bid_sweep_hot_kernel + sslapb_bid_sweep_redo_kernel (full frontier, N bidders, merge atomics on; "
+                                   "timed as a pair): the bidding step as the solver runs it — hot list first (512 B per row, 32 registers, "
+                                   "64 warps per SM), full CSR row for the bidders that is not provably exact for", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": f"{traffic_src} (ncu --set full of this launch: "
                          "dram__bytes_read.sum + dram__bytes_write.sum)" if traffic_src else None,
                          "bytes_per_launch": sweep_bytes, "avg_launch_us": avg.value * 1e3,
                          "bytes_note": "algorithmic bytes = 12 B x entries of the bidders' rows + 36 B x bidders (SURVEY.md 8d); the hot form "
                                        "reads fewer (see traffic): it skips row entries it can prove irrelevant",
+                         "clean_l2_flush": {"what": "same launch pair, L2 flushed by the memset AND a 256 MB read pass (the memset alone leaves "
+                                                    "126 MB of dirty lines whose write-back is charged to the kernel)",
+                                            "avg_launch_us": avg_clean.value * 1e3, "achieved": sweep_bytes / (avg_clean.value * 1e-3) / 1e9,
+                                            "frac": sweep_bytes / (avg_clean.value * 1e-3) / 1e9 / peak},
                          "streaming_only": {"kernel": "sslapb_bid_sweep_kernel: every row read in full (round 1's roofline kernel)",
                                             "achieved": achieved_stream, "frac": achieved_stream / peak, "avg_launch_us": avg_stream.value * 1e3,
                                             "traffic": traffic_stream, "traffic_source": traffic_stream_src},

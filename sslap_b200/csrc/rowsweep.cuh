@@ -311,11 +311,24 @@ __device__ __forceinline__ SslapbBid row_bid_pruned_lean(const SslapbStreamChunk
 // Bid of one person from its hot list (hot.cu): lane t holds hot entry t; one price gather per lane, no per-lane
 // tournament.  Exact when the second-best value found is strictly above `rest` (the bound of everything outside the
 // list), or when nothing is outside (rest = -inf); otherwise j = -1 sends the caller to the full-row sweep.
+struct SslapbHotIn { int4 q; double rest; };                  // lane t: hot entry t of the person + the row's bound
+__device__ __forceinline__ SslapbHotIn sslapb_hot_in(const SslapbHotEnt *__restrict__ hot, const double *rest_arr, int person, int lane)
+{
+    SslapbHotIn in;
+    in.q = __ldg(reinterpret_cast<const int4 *>(hot) + (long long)person * 32 + lane);
+    in.rest = rest_arr[person];
+    return in;
+}
+__device__ __forceinline__ SslapbBid row_bid_hot_from(const SslapbHotIn &in, const double *price, int lane, double eps);
 __device__ __forceinline__ SslapbBid row_bid_hot(const SslapbHotEnt *__restrict__ hot, const double *rest_arr, const double *price,
                                                  int person, int lane, double eps)
 {
-    const int4 q = __ldg(reinterpret_cast<const int4 *>(hot) + (long long)person * 32 + lane);
-    const double rest = rest_arr[person];
+    return row_bid_hot_from(sslapb_hot_in(hot, rest_arr, person, lane), price, lane, eps);
+}
+__device__ __forceinline__ SslapbBid row_bid_hot_from(const SslapbHotIn &in, const double *price, int lane, double eps)
+{
+    const int4 q = in.q;
+    const double rest = in.rest;
     const double a = __hiloint2double(q.w, q.z);
     const double v = a - price[q.x];                           // padding: column 0, a = -inf -> v = -inf
     const bool has = v > SSLAPB_NEG_INF;                       // real -inf candidates: left to the generic sweep

@@ -25,5 +25,8 @@ variants = [("4 rows/warp, 8 lanes/row", 1 | 128), ("4 rows/warp, pruning off", 
 for rep in range(2):
     for name, merge in variants:
         ms = C.c_float(0)
-        rc = L.sslapb_bid_sweep(h.ptr, None, None, n, 1e-5, merge, iters, 1, None, None, C.byref(ms))
-        print(f"rep{rep} {name:42s} rc={rc} {ms.value*1e3:7.1f} us  {by/ms.value/1e6:7.0f} GB/s  frac={by/ms.value/1e6/peak:.3f}", flush=True)
+        out = []
+        for fl in (1, 2):                                   # 1: L2 flushed by a 256 MB memset; 2: memset + 256 MB read (clean lines)
+            rc = L.sslapb_bid_sweep(h.ptr, None, None, n, 1e-5, merge, iters, fl, None, None, C.byref(ms))
+            out.append(f"flush{fl}: {ms.value*1e3:6.1f} us {by/ms.value/1e6:6.0f} GB/s frac={by/ms.value/1e6/peak:.3f}")
+        print(f"rep{rep} {name:42s} rc={rc}  " + "   ".join(out), flush=True)
