@@ -43,6 +43,7 @@ cudaError_t sslapb_launch_bid_sweep2(const SslapbAuctionParams *, const int *, i
 cudaError_t sslapb_launch_bid_sweep4(const SslapbAuctionParams *, const int *, int, float, int, int, cudaStream_t);
 cudaError_t sslapb_launch_bid_sweep_hot(const SslapbAuctionParams *, const int *, int, float, int, int, cudaStream_t);
 cudaError_t sslapb_launch_hot_rest(const SslapbAuctionParams *, int, cudaStream_t);
+cudaError_t sslapb_launch_bid_sweep_lean(const SslapbAuctionParams *, const int *, int, float, int, int, cudaStream_t);
 cudaError_t sslapb_hk_launch_greedy(const long long *, const int *, int, int *, int *, SslapbHkFlags *, int, cudaStream_t);
 cudaError_t sslapb_hk_launch_phase_init(int, int, const int *, int *, int *, int *, int *, SslapbHkFlags *, int, cudaStream_t);
 cudaError_t sslapb_hk_launch_bfs_level(const long long *, const int *, int, int, const int *, int *, int *, int *, int *,
@@ -938,6 +939,8 @@ extern "C" int sslapb_bid_sweep(sslapb_handle *h, const double *prices, const in
     // bit 8: hot form — every bidder from its hot list when provably exact (bounds taken at the prices of this call), else
     // the full-row sweep; what the persistent kernel's grid regime runs from the third eps-phase on
     const bool hot_form = (merge & 256) != 0 && h->N > 32 && !streamed;
+    // bit 9: the lean full-row sweep (sweep_lean.cu: 40 registers, redo list for the uncommon rows) — every row read in full
+    const bool lean_form = (merge & 512) != 0 && !streamed && !hot_form;
     if (hot_form) {
         rc = attach_hot_lists(h, P, nullptr, nullptr);
         if (rc) return rc;
@@ -959,7 +962,7 @@ extern "C" int sslapb_bid_sweep(sslapb_handle *h, const double *prices, const in
     float total = 0.f;
     for (int it = 0; it < iters; ++it) {
         if (merge) CK(cudaMemsetAsync(P.bidkey, 0, (size_t)h->M * 8, h->stream));
-        if (hot_form) CK(cudaMemsetAsync(&P.ctrl->hot_probe_fail, 0, sizeof(int), h->stream));   // redo counter of the hot-form pair
+        if (hot_form || lean_form) CK(cudaMemsetAsync(&P.ctrl->hot_probe_fail, 0, sizeof(int), h->stream));   // redo counter of the launch pairs
         if (flush_l2) {
             CK(cudaMemsetAsync(h->flush.p, it & 0xff, flush_bytes, h->stream));
             if (flush_l2 > 1)                                  // 2: memset, then a read pass (clean lines, see sslapb_l2_drain_kernel)
@@ -969,6 +972,7 @@ extern "C" int sslapb_bid_sweep(sslapb_handle *h, const double *prices, const in
         CK(cudaEventRecord(h->ev[3], h->stream));
         if (streamed) CK(sslapb_launch_bid_sweep_tma(&P, h->sweep_plan.as<int>(), eps, merge, h->sms, h->stream));
         else if (hot_form) CK(sslapb_launch_bid_sweep_hot(&P, d_bidders, nb, eps, merge, h->sms, h->stream));
+        else if (lean_form) CK(sslapb_launch_bid_sweep_lean(&P, d_bidders, nb, eps, merge, h->sms, h->stream));
         else if (per_row) CK(sslapb_launch_bid_sweep(&P, d_bidders, nb, eps, merge, h->sms, h->stream));
         else if (pipelined) CK(sslapb_launch_bid_sweep2(&P, d_bidders, nb, eps, merge, threads2, lean2, h->sms, h->stream));
         else CK(sslapb_launch_bid_sweep4(&P, d_bidders, nb, eps, merge, h->sms, h->stream));

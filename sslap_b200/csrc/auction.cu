@@ -1923,6 +1923,13 @@ extern "C" cudaError_t sslapb_launch_hot_rest(const SslapbAuctionParams *P, int 
     return cudaGetLastError();
 }
 
+extern "C" cudaError_t sslapb_launch_bid_sweep_redo(const SslapbAuctionParams *P, const int *bidders, float eps, int merge,
+                                                    int grid, cudaStream_t stream)
+{
+    sslapb_bid_sweep_redo_kernel<<<grid * 2, 512, 0, stream>>>(*P, bidders, eps, merge);
+    return cudaGetLastError();
+}
+
 extern "C" cudaError_t sslapb_launch_bid_sweep_hot(const SslapbAuctionParams *P, const int *bidders, int nb, float eps,
                                                    int merge, int grid, cudaStream_t stream)
 {

@@ -131,7 +131,7 @@ def test_bid_sweep_streamed_bit_exact(gpu, oracle_mod):
                 prices = rng.uniform(0, 5, M)
                 prices[rng.integers(0, M, max(1, M // 50))] = np.inf
             oj, ob = oracle_mod.bid_sweep(rowptr, loc[:, 1], -val, prices, np.arange(n, dtype=np.int32), 0.37)
-            for merge in (0, 2, 4, 6, 128, 130, 8, 10, 8 | 16, 8 | 32 | 2, 8 | 48, 8 | 64, 256, 258):   # per-row (default), TMA ring, 4 rows/warp, pipelined, hot form
+            for merge in (0, 2, 4, 6, 128, 130, 8, 10, 8 | 16, 8 | 32 | 2, 8 | 48, 8 | 64, 256, 258, 512, 514):   # per-row (default), TMA ring, 4 rows/warp, pipelined, hot form, lean
                 jb = np.empty(n, dtype=np.int32)
                 bd = np.empty(n, dtype=np.float64)
                 ms = C.c_float(0)

@@ -21,7 +21,8 @@ by = 12 * val.size + 36 * n
 variants = [("4 rows/warp, 8 lanes/row", 1 | 128), ("4 rows/warp, pruning off", 3 | 128),
             ("per-row kernel (default)", 1), ("per-row kernel, pruning off", 3),
             ("pipelined per-row 768 thr", 1 | 8), ("pipelined per-row 1024 thr", 1 | 8 | 16), ("TMA ring", 1 | 4),
-            ("hot form (hot lists + exact fallback)", 1 | 256)]
+            ("hot form (hot lists + exact fallback)", 1 | 256),
+            ("lean full-row sweep + redo list", 1 | 512), ("lean full-row sweep, pruning off", 3 | 512)]
 for rep in range(2):
     for name, merge in variants:
         ms = C.c_float(0)
