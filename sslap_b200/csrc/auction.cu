@@ -1858,6 +1858,8 @@ __global__ void __launch_bounds__(1024, 2) sslapb_bid_sweep_hot_kernel(SslapbAuc
             else P.mover[atomicAdd(&P.ctrl->hot_probe_fail, 1)] = a;
         }
     }
+    // programmatic dependent launch: the redo pass may be scheduled while this grid drains (it waits for our writes itself)
+    asm volatile("griddepcontrol.launch_dependents;");
 }
 
 // Pass 2: the redo list through the full-row sweep (bound-pruned, exact) — the per-row kernel's body.
@@ -1868,6 +1870,7 @@ __global__ void __launch_bounds__(512, 2) sslapb_bid_sweep_redo_kernel(SslapbAuc
     const int wpc = blockDim.x >> 5;
     const int gwarp = blockIdx.x * wpc + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * wpc;
+    asm volatile("griddepcontrol.wait;" ::: "memory");        // the pass that wrote the redo list has completed and is visible
     const int nredo = *(volatile int *)&P.ctrl->hot_probe_fail;
     if (gwarp >= nredo) return;
     const double eps = (double)eps_f;
@@ -1926,8 +1929,13 @@ extern "C" cudaError_t sslapb_launch_hot_rest(const SslapbAuctionParams *P, int 
 extern "C" cudaError_t sslapb_launch_bid_sweep_redo(const SslapbAuctionParams *P, const int *bidders, float eps, int merge,
                                                     int grid, cudaStream_t stream)
 {
-    sslapb_bid_sweep_redo_kernel<<<grid * 2, 512, 0, stream>>>(*P, bidders, eps, merge);
-    return cudaGetLastError();
+    // launched with programmatic stream serialization: its CTAs may be scheduled while the producing pass drains
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid * 2); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, sslapb_bid_sweep_redo_kernel, *P, bidders, eps, merge);
 }
 
 extern "C" cudaError_t sslapb_launch_bid_sweep_hot(const SslapbAuctionParams *P, const int *bidders, int nb, float eps,

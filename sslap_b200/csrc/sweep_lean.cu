@@ -108,6 +108,9 @@ __global__ void __launch_bounds__(512, 3) sslapb_bid_sweep_lean_kernel(SslapbAuc
             }
         }
     }
+    asm volatile("griddepcontrol.launch_dependents;");         // see sslapb_launch_bid_sweep_redo
+    // (rows of more than one warp pass folded in here by a loop over trips — instead of the redo list — spill at 40 registers
+    // and cost 60 us: measured and dropped)
 }
 
 extern "C" cudaError_t sslapb_launch_bid_sweep_redo(const SslapbAuctionParams *P, const int *bidders, float eps, int merge,
