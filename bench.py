@@ -276,15 +276,17 @@ def main():
     # ---------------- roofline of the dominant-bandwidth kernel: the full-frontier bidding sweep ----------------
     # The product's sweep = hot form (merge bit 8): every bidder from its hot list when provably exact, else the full row;
     # the streaming-only kernel (every row read in full, round 1's roofline kernel) is timed beside it.
-    avg, avg_stream, avg_clean = C.c_float(0), C.c_float(0), C.c_float(0)
+    avg, avg_stream, avg_clean, avg_lean = C.c_float(0), C.c_float(0), C.c_float(0), C.c_float(0)
     eps_sw = float(np.float32(1.0 / N_ROWS))
-    for variant in (1 | 256, 1):                                            # untimed first launches (lazy module load)
+    for variant in (1 | 256, 1, 1 | 512):                                   # untimed first launches (lazy module load)
         assert L.sslapb_bid_sweep(h.ptr, None, None, N_ROWS, eps_sw, variant, 3, 1, None, None, C.byref(avg)) == 0
     rc = L.sslapb_bid_sweep(h.ptr, None, None, N_ROWS, eps_sw, 1 | 256, 20, 1, None, None, C.byref(avg))
     assert rc == 0
     rc = L.sslapb_bid_sweep(h.ptr, None, None, N_ROWS, eps_sw, 1, 20, 1, None, None, C.byref(avg_stream))
     assert rc == 0
     rc = L.sslapb_bid_sweep(h.ptr, None, None, N_ROWS, eps_sw, 1 | 256, 20, 2, None, None, C.byref(avg_clean))
+    assert rc == 0
+    rc = L.sslapb_bid_sweep(h.ptr, None, None, N_ROWS, eps_sw, 1 | 512, 20, 1, None, None, C.byref(avg_lean))
     assert rc == 0
     sweep_bytes = 12 * nnz + 36 * N_ROWS               # SURVEY.md §8(d) / DESIGN.md §4.2: 12 B per CSR entry + 36 B per bidder
     peak, peak_src = measured_peaks()
@@ -372,7 +374,10 @@ def main():
                                             "frac": sweep_bytes / (avg_clean.value * 1e-3) / 1e9 / peak},
                          "streaming_only": {"kernel": "sslapb_bid_sweep_kernel: every row read in full (round 1's roofline kernel)",
                                             "achieved": achieved_stream, "frac": achieved_stream / peak, "avg_launch_us": avg_stream.value * 1e3,
-                                            "traffic": traffic_stream, "traffic_source": traffic_stream_src},
+                                            "traffic": traffic_stream, "traffic_source": traffic_stream_src,
+                                            "lean_schedule": {"kernel": "sslapb_bid_sweep_lean_kernel + redo pass: every row read in full, 40 registers",
+                                                              "avg_launch_us": avg_lean.value * 1e3,
+                                                              "frac": sweep_bytes / (avg_lean.value * 1e-3) / 1e9 / peak}},
                          "insitu": {"what": "bidding step of the full-frontier rounds inside the persistent kernel (512-thread CTAs, "
                                             "globaltimer, incl. the grid barrier that ends the step); at N>1 each rank sweeps 1/N of the rows",
                                     "avg_us": float(np.mean(insitu_us)), "rounds_per_solve": int(meta.sweep_insitu_n),
