@@ -90,8 +90,7 @@ __device__ __forceinline__ int warp_resolve(const SslapbAuctionParams &P, int nu
         sslapb_st_rec256(P.rec + j, (unsigned long long)lst, ((unsigned long long)(unsigned)ldg << 32) | (unsigned)li,
                          (unsigned long long)__double_as_longlong(bid));   // owner + its row (:418), price (:397)
         P.price[j] = bid;
-        P.p2o[li] = j;                                         // :417
-        if (B.powner >= 0) P.p2o[B.powner] = -1;               // :404
+        // (person_to_object, :404 / :417, is not kept up to date round by round: rebuild_p2o derives it from the records)
         nv = B.powner;                                         // evicted owner takes the slot (:409) or hole (:412)
         nst = B.pstart; ndg = B.pdeg;
     }
@@ -311,8 +310,10 @@ __device__ __forceinline__ void commit_win(const SslapbAuctionParams &P, int per
     sslapb_st_rec256(P.rec + B.j, (unsigned long long)st, ((unsigned long long)(unsigned)dg << 32) | (unsigned)person,
                      (unsigned long long)__double_as_longlong(B.bid));   // owner + its row (:418), price (:397)
     P.price[B.j] = B.bid;
-    P.p2o[person] = B.j;                                       // :417
-    if (B.powner >= 0) P.p2o[B.powner] = -1;                   // :404
+    // person_to_object (:404, :417) is NOT written here: nothing reads it inside an eps-phase, and two of a commit's four
+    // stores (with their address arithmetic) are a measurable share of a single-warp round — rebuild_p2o derives it from
+    // the records' owners before every eps-CS sweep and in the epilogue
+    (void)person;
 }
 
 // Single-bidder chain (52 % of all rounds at N = 100k): person i bids, wins (there is no competitor), evicts the owner i'
@@ -1429,8 +1430,7 @@ __device__ __forceinline__ int spread_round(const SslapbAuctionParams &P, Sslapb
             sslapb_st_rec256(P.rec + j, (unsigned long long)rst, ((unsigned long long)(unsigned)rdg << 32) | (unsigned)i,
                              (unsigned long long)__double_as_longlong(bid));
             P.price[j] = bid;
-            P.p2o[i] = j;
-            if (prev >= 0) P.p2o[prev] = -1; else ++myholes;
+            if (prev < 0) ++myholes;                   // (person_to_object: see rebuild_p2o)
             P.list[a] = prev;                          // evicted owner takes the slot, or -1 = hole
             P.bidkey[j] = 0ull;
             if (tie) P.winpos[j] = 0x7fffffff;
@@ -1559,6 +1559,17 @@ __device__ __forceinline__ int spread_round(const SslapbAuctionParams &P, Sslapb
 
 #define GB() do { if (!grid_barrier(C, nblk, bar_epoch, P.watchdog_ns)) return; } while (0)
 
+// person_to_object (auction_.pyx:231) from object_to_person: every owned object names its person.  Called by all CTAs right
+// after a grid barrier; the caller follows it with another one.  `clear` first resets every person (needed when some are
+// unassigned: max_iter hit inside a phase); with a full assignment every entry is overwritten anyway.
+__device__ __forceinline__ void rebuild_p2o_owners(const SslapbAuctionParams &P, int gtid, int nthreads)
+{
+    for (int j = gtid; j < P.M; j += nthreads) {
+        const int o = P.rec[j].owner;
+        if (o >= 0) P.p2o[o] = j;
+    }
+}
+
 #ifdef SSLAPB_LONG_ROWS
 #define sslapb_auction_kernel sslapb_auction_kernel_long   // second instance of the kernel, see auction_long.cu
 #endif
@@ -1642,6 +1653,8 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
             const float teps = *(volatile float *)&C->target_eps;
             const double eps_t = (double)teps, tol = *(volatile double *)&C->tol;
             bool viol = false;
+            rebuild_p2o_owners(P, gtid, nthreads);             // nu == 0: every person owns exactly one object
+            GB();
             for (int i = gwarp; i < P.N; i += nwarps) {        // eCE_satisfied(target_eps), :443-485
                 const int j = P.p2o[i];
                 const long long st = __ldg(P.rowptr + i), en = __ldg(P.rowptr + i + 1);
@@ -1708,6 +1721,10 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
         const bool need_ece = (*(volatile int *)&C->ece_final < 0) && nu == 0;   // max_iter hit on a full assignment
         const double eps_t = (double)(*(volatile float *)&C->target_eps), tol = *(volatile double *)&C->tol;
         bool viol = false;
+        for (int i = gtid; i < P.N; i += nthreads) P.p2o[i] = -1;              // the final person_to_object (`sol`)
+        GB();
+        rebuild_p2o_owners(P, gtid, nthreads);
+        GB();
         for (int i = gwarp; i < P.N; i += nwarps) {
             const int j = P.p2o[i];
             double csum = 0.0;
