@@ -20,6 +20,15 @@
 //             long rows).
 //   2         warps 0 and 1 of CTA 0 (duo rounds inside multi_rounds).
 //   1         warp 0 of CTA 0, no barrier at all (chain_rounds; coop_chain_rounds when the row is long).
+// Round 2, on top of the regimes:
+//   hot lists     (hot.cu) every regime first tries to decide a bid from the person's 32 largest entries (512 bytes, one
+//                 gather per lane) and falls back to the full row when that is not provably exact; switched on and off
+//                 per eps-phase by the measured share of undecided bids (row_bid_hot, sweep_hot, *_rounds_hot);
+//   no-hole exit  a grid round in which no unowned object was won and no equal bids were seen ends after its second
+//                 barrier (no compaction, no final barrier); frontiers of at most 512 are compacted by CTA 0 alone;
+//   lean loops    the single-warp loops are bound by instruction latency, not memory: the chain loop of
+//                 the decided rounds carries no fallback code and is unrolled by two;
+//   person_to_object is rebuilt from the records' owners when it is needed (rebuild_p2o_owners), not kept per round.
 // This file is compiled three times (plain, SSLAPB_LONG_ROWS, SSLAPB_SHARDED): see the two wrapper units.  (Round 1's
 // opt-in cluster regime — mid-sized frontiers on one 8-CTA cluster — was removed in round 2: DESIGN.md 4.1b.)
 #include "auction.cuh"
