@@ -1460,13 +1460,11 @@ __device__ __forceinline__ int spread_round(const SslapbAuctionParams &P, Sslapb
     if (!grid_barrier(C, (unsigned)S.nblk, bar_epoch, P.watchdog_ns)) return 0;
     if (S.lead) tp4 = sslapb_globaltimer();
     // (3) push_all_left (:137-162): k-th hole left of new_nu <- k-th live entry right of it
-    int sr_v = 0, sr_before = 0;
+    int sr_v = 0, sr_total = 0;
     bool sr_hole = false;
     if (small_round) {
         if (tid < nu) { sr_v = P.list[tid]; sr_hole = sr_v < 0; }
-        int tot;
-        sr_before = block_excl_scan_flag(sr_hole, tot);
-        if (tid == 0) { s_hpre[2] = tot; s_hpre[1] = 0; s_hpre[0] = 0; s_red = 0; }
+        sr_total = __syncthreads_count(sr_hole);       // ONE barrier instruction: every CTA knows H (most rounds have none)
     } else
     if (warp == 0) {                                   // per-CTA hole counts -> total, my prefix, prefix of the split chunk
         int ht = 0, hp = 0;
@@ -1487,8 +1485,9 @@ __device__ __forceinline__ int spread_round(const SslapbAuctionParams &P, Sslapb
         for (int off = 16; off > 0; off >>= 1) h2 += __shfl_xor_sync(SSLAPB_FULL, h2, off);
         if (lane == 0) { s_hpre[0] = h2; s_hpre[1] = hp; s_hpre[2] = ht; s_red = 0; }
     }
-    __syncthreads();
-    const int H = __shfl_sync(SSLAPB_FULL, s_hpre[2], 0), hpre = __shfl_sync(SSLAPB_FULL, s_hpre[1], 0);
+    if (!small_round) __syncthreads();
+    const int H = small_round ? sr_total : __shfl_sync(SSLAPB_FULL, s_hpre[2], 0);
+    const int hpre = small_round ? 0 : __shfl_sync(SSLAPB_FULL, s_hpre[1], 0);
     if (H == 0 && !tie && !hot_probe && its + 2 < max_iter) {  // no hole, no tie: nothing to compact, nothing to reset
         if (S.lead) {
             C->its = its + 1;
@@ -1507,8 +1506,10 @@ __device__ __forceinline__ int spread_round(const SslapbAuctionParams &P, Sslapb
     }
     const int new_nu = nu - H;
     if (small_round) {
-        if (S.blk == 0) {                              // thread t = position t; holes before position new_nu = Hsplit
-            if (tid == new_nu) s_hpre[0] = sr_before;  // (new_nu < nu <= blockDim whenever there is a hole; else nothing moves)
+        if (S.blk == 0 && H > 0) {                     // thread t = position t; holes before position new_nu = Hsplit
+            int tot2;
+            const int sr_before = block_excl_scan_flag(sr_hole, tot2);
+            if (tid == new_nu) s_hpre[0] = sr_before;  // (new_nu < nu <= blockDim whenever there is a hole)
             __syncthreads();
             const int Hsplit = new_nu < nu ? s_hpre[0] : H;
             if (tid < nu) {
