@@ -69,7 +69,8 @@ typedef struct sslapb_meta {
                                 eCE + phase change, (unused), grid barriers */
     int64_t prune_second_pass; /* grid-regime rows whose bound-pruned sweep needed the second (exactness) gather pass */
     int32_t stop_reason;     /* 1 target-eps CS holds (:275) | 2 eps < target (:280) | 3 max_iter (:309) */
-    int32_t rounds_cluster;  /* always 0 (round 1's opt-in cluster regime was removed; the field keeps the layout) */
+    int32_t small_path;      /* 1 when the single-launch path for small problems ran (small.cu); the field replaces round 1's
+                                rounds_cluster, same size and place */
     /* ---- ABI version 2 ---- */
     int32_t n_ranks, rank;   /* row-sharded solve (sslapb_comm_init): size of the communicator and this handle's rank; 1, 0 otherwise */
     int32_t row_lo, row_hi;  /* ... the nnz-balanced row range [row_lo, row_hi) this rank bids for in sharded rounds */
@@ -101,6 +102,8 @@ int    sslapb_abi_version(void);
    "hk_host_loop" (1: Hopcroft-Karp phases driven from the host with one read-back per BFS level, as in round 1, instead of the
    device-resident loop; A/B runs; default 0),
    "batch_v1" (1: round 1's batch kernel — a whole warp sweeps one bidder at a time — instead of the sub-warp kernel; A/B runs),
+   "small_path" (0: never take the single-launch path for small problems — N, M <= 256 and <= 12288 entries, host buffers; tests
+   of the general path on small inputs; default 1),
    "hot" (0: never decide bids from the hot lists — A/B runs; default 1),
    "l2_persist" (1: persisting L2 access-policy window over the hot lists during a solve — A/B runs; measured no gain; default 0),
    "coop" (row-sharded solves only; 0: launch the persistent kernel without the cooperative attribute so that several of them

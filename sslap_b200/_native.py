@@ -32,7 +32,7 @@ class Meta(C.Structure):
                 ("cardinality", C.c_int32), ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("nnz", C.c_int64),
                 ("rounds_grid", C.c_int64), ("rounds_warp", C.c_int64), ("rounds_solo", C.c_int64),
                 ("prof_ms", C.c_float * 8), ("prune_second_pass", C.c_int64),
-                ("stop_reason", C.c_int32), ("rounds_cluster", C.c_int32),
+                ("stop_reason", C.c_int32), ("small_path", C.c_int32),
                 ("n_ranks", C.c_int32), ("rank", C.c_int32), ("row_lo", C.c_int32), ("row_hi", C.c_int32),
                 ("rounds_sharded", C.c_int64), ("xchg_ms", C.c_float), ("sharded_ms", C.c_float),
                 ("sweep_insitu_us", C.c_float), ("sweep_insitu_n", C.c_int32), ("warm_start", C.c_int32),

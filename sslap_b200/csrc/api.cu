@@ -3,6 +3,7 @@
 #include "../../include/sslap_b200.h"
 #include "auction.cuh"
 #include "build.cuh"
+#include "small.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -43,6 +44,7 @@ cudaError_t sslapb_launch_bid_sweep2(const SslapbAuctionParams *, const int *, i
 cudaError_t sslapb_launch_bid_sweep4(const SslapbAuctionParams *, const int *, int, float, int, int, cudaStream_t);
 cudaError_t sslapb_launch_bid_sweep_hot(const SslapbAuctionParams *, const int *, int, float, int, int, cudaStream_t);
 cudaError_t sslapb_launch_hot_rest(const SslapbAuctionParams *, int, cudaStream_t);
+cudaError_t sslapb_launch_small(const SslapbSmallArgs *, cudaStream_t);
 cudaError_t sslapb_launch_bid_sweep_lean(const SslapbAuctionParams *, const int *, int, float, int, int, cudaStream_t);
 cudaError_t sslapb_hk_launch_greedy(const long long *, const int *, int, int *, int *, SslapbHkFlags *, int, cudaStream_t);
 cudaError_t sslapb_hk_launch_phase_init(int, int, const int *, int *, int *, int *, int *, SslapbHkFlags *, int, cudaStream_t);
@@ -122,6 +124,8 @@ struct sslapb_handle {
     int strict = 0;                // strict-optimality stop rule (see the header)
     int coop = 1;                  // 0: launch the row-sharded persistent kernel without the cooperative attribute (virtual ranks)
     int hot = 1;                   // hot lists (hot.cu): 0 = off (A/B runs)
+    int small_path = 1;            // single-launch path for small problems (small.cu): 0 = off
+    int small_max_n = 128;         // ... taken for N, M up to this (measured: it wins up to the dense 110 x 110 that fits; the kernel holds up to SSLAPB_SMALL_MAXN)
     int l2_persist = 0;            // 1: L2 access-policy window (persisting) over the hot lists during a solve (measured: no gain at C3,
                                    // 233.0 vs 233.1 ms — the lists stay in L2 on their own; kept for A/B runs)
     size_t l2_persist_max = 0;     // cudaDevAttrMaxPersistingL2CacheSize
@@ -241,6 +245,8 @@ extern "C" int sslapb_set_option(sslapb_handle *h, const char *name, int64_t val
     if (!strcmp(name, "hk_host_loop")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->hk_host_loop = (int)value; return 0; }
     if (!strcmp(name, "batch_v1")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->batch_v1 = (int)value; return 0; }
     if (!strcmp(name, "l2_persist")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->l2_persist = (int)value; return 0; }
+    if (!strcmp(name, "small_max_n")) { if (value < 1 || value > SSLAPB_SMALL_MAXN) return SSLAPB_E_BAD_ARG; h->small_max_n = (int)value; return 0; }
+    if (!strcmp(name, "small_path")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->small_path = (int)value; return 0; }
     if (!strcmp(name, "hot")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->hot = (int)value; return 0; }
     if (!strcmp(name, "coop")) { if (value < 0 || value > 1) return SSLAPB_E_BAD_ARG; h->coop = (int)value; return 0; }
     return fail(h, SSLAPB_E_BAD_ARG, std::string("unknown option ") + name);
@@ -638,7 +644,7 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
         cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); meta->h2d_ms = ms;
         meta->n_rows = h->N; meta->n_cols = h->M; meta->nnz = h->nnz;
         meta->rounds_grid = c.rounds_grid; meta->rounds_warp = c.rounds_warp; meta->rounds_solo = c.rounds_solo;
-        meta->rounds_cluster = 0;                              // (the cluster regime was removed in round 2)
+        meta->small_path = 0;
         for (int k = 0; k < 8; ++k) meta->prof_ms[k] = (float)((double)c.prof[k] * 1e-6);
         meta->stop_reason = c.done;
         meta->prune_second_pass = c.prune_second_pass;
@@ -684,6 +690,80 @@ static int solve_resident(sslapb_handle *h, const SslapbBuildFlags &F, int maxim
     return rc;
 }
 
+// ----------------------------------------------------------------------------------------------------------------------
+// Small problems: one H2D copy, ONE launch (small.cu: build + feasibility + auction in shared memory), one D2H copy.
+// *handled = false: not eligible (or the kernel sent the input to the general path: unsorted / out of range / too many
+// valid entries) — the caller continues as before.  The resident CSR of the handle is invalidated (sweeps refuse).
+// ----------------------------------------------------------------------------------------------------------------------
+static int run_small(sslapb_handle *h, const double *mat, const void *rows, const void *cols, int idx_bytes, int64_t stride,
+                     const double *val, int64_t nnz, int32_t N, int32_t M, int maximize, float eps_start, int64_t max_iter,
+                     int cardinality_check, int mem, int32_t *sol_out, sslapb_meta *meta, bool *handled)
+{
+    *handled = false;
+    // only with the default regime options: a caller that sets t_small is exercising the general path's regimes
+    if (!h->small_path || h->t_small != 32 || h->n_ranks > 1 || h->strict || h->warm_cols > 0 || mem != SSLAPB_MEM_HOST || !sol_out)
+        return SSLAPB_OK;
+    if (N < 1 || M < 1 || N > h->small_max_n || M > h->small_max_n) return SSLAPB_OK;
+    const bool dense = mat != nullptr;
+    const bool interleaved = !dense && stride == 2 && (const char *)cols == (const char *)rows + 4;
+    if (!dense && (idx_bytes != 4 || nnz < 1 || nnz > SSLAPB_SMALL_CAP || !(interleaved || stride == 1))) return SSLAPB_OK;
+    SslapbSmallArgs A;
+    memset(&A, 0, sizeof A);
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    if (dense) {
+        CK(h->stage_mat.reserve((size_t)N * M * 8));
+        CK(cudaMemcpyAsync(h->stage_mat.p, mat, (size_t)N * M * 8, cudaMemcpyHostToDevice, h->stream));
+        A.mat = h->stage_mat.as<double>(); A.dense = 1;
+    } else {
+        CK(h->stage_idx.reserve(2 * (size_t)nnz * 4));
+        CK(h->stage_val.reserve((size_t)nnz * 8));
+        int *s = h->stage_idx.as<int>();
+        if (interleaved) {
+            CK(cudaMemcpyAsync(s, rows, 2 * (size_t)nnz * 4, cudaMemcpyHostToDevice, h->stream));
+            A.rows = s; A.cols_in = s + 1; A.stride = 2;
+        } else {
+            CK(cudaMemcpyAsync(s, rows, (size_t)nnz * 4, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(s + nnz, cols, (size_t)nnz * 4, cudaMemcpyHostToDevice, h->stream));
+            A.rows = s; A.cols_in = s + nnz; A.stride = 1;
+        }
+        CK(cudaMemcpyAsync(h->stage_val.p, val, (size_t)nnz * 8, cudaMemcpyHostToDevice, h->stream));
+        A.val = h->stage_val.as<double>(); A.nnz = (int)nnz;
+    }
+    CK(h->price.reserve((size_t)M * 8)); CK(h->p2o.reserve((size_t)N * 4)); CK(h->ctrl.reserve(sizeof(SslapbCtrl)));
+    static_assert(sizeof(SslapbSmallResult) <= sizeof(SslapbCtrl), "result block fits the control buffer");
+    A.N = N; A.M = M; A.negate = !maximize; A.hk = cardinality_check ? 1 : 0; A.eps_start = eps_start; A.max_iter = max_iter;
+    A.sol_out = h->p2o.as<int>(); A.price_out = h->price.as<double>(); A.res = h->ctrl.as<SslapbSmallResult>();
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(sslapb_launch_small(&A, h->stream));
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    SslapbSmallResult R;
+    CK(cudaMemcpyAsync(&R, A.res, sizeof R, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(sol_out, A.sol_out, (size_t)N * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (R.status == 3) return SSLAPB_OK;                       // the general path takes it
+    *handled = true;
+    h->N = N; h->M = M; h->nnz = R.nnz; h->has_vals = false; h->hot_valid = false;   // no resident CSR: prices only
+    if (meta) {
+        memset(meta, 0, sizeof *meta);
+        meta->cardinality = R.cardinality; meta->n_rows = N; meta->n_cols = M; meta->nnz = R.nnz;
+        meta->n_ranks = 1; meta->row_hi = N; meta->small_path = 1;
+    }
+    if (R.status == 1) return fail(h, SSLAPB_E_FEWER_THAN_N, "fewer valid values than rows");
+    if (R.status == 2) return fail(h, SSLAPB_E_CARDINALITY, "maximum matching smaller than the number of rows");
+    if (R.status == 6) return fail(h, SSLAPB_E_EMPTY_ROW, "a row has no valid entry");
+    if (meta) {
+        meta->start_eps = R.start_eps; meta->final_eps = R.final_eps; meta->target_eps = R.target_eps;
+        meta->eCE = R.eCE; meta->soln_found = R.soln_found; meta->its = R.its; meta->nreductions = R.nreductions;
+        meta->n_assigned = R.n_assigned; meta->obj64 = R.obj64; meta->obj = (float)R.obj64;
+        meta->stop_reason = R.its >= max_iter ? 3 : (R.eCE ? 1 : 2);
+        meta->rounds_solo = R.its;                             // (all rounds run by the one CTA)
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); meta->solve_ms = ms;
+        cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); meta->h2d_ms = ms;
+    }
+    return SSLAPB_OK;
+}
+
 extern "C" int sslapb_auction_coo(sslapb_handle *h, const void *rows, const void *cols, int idx_bytes, int64_t stride,
                                   const double *val, int64_t nnz, int32_t n_rows, int32_t n_cols, int maximize,
                                   float eps_start, int64_t max_iter, int cardinality_check, int mem, int32_t *sol_out,
@@ -693,6 +773,12 @@ extern "C" int sslapb_auction_coo(sslapb_handle *h, const void *rows, const void
     LOCK(h);
     if (!val) return fail(h, SSLAPB_E_BAD_ARG, "val is NULL");
     CK(cudaSetDevice(h->device));
+    {
+        bool handled = false;
+        int rs = run_small(h, nullptr, rows, cols, idx_bytes, stride, val, nnz, n_rows, n_cols, maximize, eps_start, max_iter,
+                           cardinality_check, mem, sol_out, meta, &handled);
+        if (rs || handled) return rs;
+    }
     SslapbBuildFlags F;
     memset(&F, 0, sizeof F);
     if (nnz == 0) return fail(h, SSLAPB_E_FEWER_THAN_N, "no entries");
@@ -708,6 +794,18 @@ extern "C" int sslapb_auction_dense(sslapb_handle *h, const double *mat, int32_t
     if (!h) return SSLAPB_E_BAD_ARG;
     LOCK(h);
     CK(cudaSetDevice(h->device));
+    bool small_fits = mat && (long long)n_rows * n_cols <= 4ll * SSLAPB_SMALL_CAP && mem == SSLAPB_MEM_HOST;
+    if (small_fits && (long long)n_rows * n_cols > SSLAPB_SMALL_CAP) {        // count the valid entries before trying (a few microseconds)
+        long long cnt = 0;
+        for (long long k = 0, e = (long long)n_rows * n_cols; k < e; ++k) cnt += mat[k] >= 0.0;
+        small_fits = cnt <= SSLAPB_SMALL_CAP;
+    }
+    if (small_fits) {
+        bool handled = false;
+        int rs = run_small(h, mat, nullptr, nullptr, 0, 0, nullptr, 0, n_rows, n_cols, maximize, eps_start, max_iter,
+                           cardinality_check, mem, sol_out, meta, &handled);
+        if (rs || handled) return rs;
+    }
     SslapbBuildFlags F;
     memset(&F, 0, sizeof F);
     int rc = build_from_dense(h, mat, n_rows, n_cols, !maximize, mem, true, F);

@@ -360,3 +360,67 @@ def test_hopcroft_device_loop_matches_host_loop_and_scipy(gpu, oracle_mod):
         assert sizes == [card, card], (n, m, sizes, card)
         if n <= 100000:
             assert oracle_mod.hopcroft_solve(loc=loc)["size"] == card
+
+
+def test_small_problems_take_the_single_launch_path(gpu, oracle_mod):
+    """csrc/small.cu: N, M <= 256 and <= 12288 entries are built, checked for feasibility and solved by ONE kernel launch
+    with everything in shared memory — and must give the oracle's sol / meta / float64 prices bit for bit, for dense and
+    COO input, int32 and int64 indices (int64 goes to the general path), rectangular shapes, heavy ties, eps_start, max_iter,
+    infeasible inputs (the reference's two ValueErrors) and unsorted input (handed to the general path, which sorts)."""
+    sslap_b200, nat, h = gpu
+    rng = np.random.default_rng(2025)
+    n_small = 0
+    h.set_option("small_max_n", 256)                                         # default 128 (where it pays); the kernel holds 256
+    for case in range(160):
+        n = int(rng.integers(2, 200))
+        m = n + int(rng.integers(0, 40)) if rng.random() < 0.3 else n
+        density = float(rng.choice([0.05, 0.1, 0.3, 0.7, 1.0]))
+        mode = "int" if rng.random() < 0.5 else "float"
+        loc, val = make_problem(n, density, mode, seed=5000 + case, m=m)
+        if rng.random() < 0.3:
+            val = np.round(val / 10.0)
+        problem = "min" if rng.random() < 0.5 else "max"
+        kw = {}
+        r = rng.random()
+        if r < 0.15:
+            kw["eps_start"] = float(rng.choice([0.5, 3.0, 40.0]))
+        elif r < 0.3:
+            kw["max_iter"] = int(rng.integers(1, 300))
+        want = oracle_mod.auction_solve(loc=loc, val=val, problem=problem, return_prices=True, **kw)
+        use_dense = rng.random() < 0.4 and (val >= 0).all()
+        if use_dense:
+            mat = -np.ones((n, m))
+            mat[loc[:, 0], loc[:, 1]] = val
+            got = sslap_b200.auction_solve(mat=mat, problem=problem, cardinality_check=bool(case % 2), _raw_meta=True,
+                                           return_prices=True, **kw)
+        else:
+            got = sslap_b200.auction_solve(loc=loc if case % 3 else loc.astype(np.int64), val=val, size=(n, m), problem=problem,
+                                           cardinality_check=bool(case % 2), _raw_meta=True, return_prices=True, **kw)
+        n_small += int(got["raw"].small_path)
+        if len(val) <= 12288 and (use_dense or case % 3):
+            assert got["raw"].small_path == 1, (case, n, m, len(val))
+        assert np.array_equal(got["sol"], want["sol"]), (case, n, m, density, mode, problem, kw)
+        assert_meta_equal(got["meta"], want["meta"])
+        assert np.array_equal(got["prices"][:want["prices"].size], want["prices"]), (case, "prices")
+    assert n_small >= 80
+    h.set_option("small_max_n", 128)
+    # the reference's two infeasibility errors, raised from the single-launch path
+    mat = -np.ones((3, 3))
+    mat[0, 0] = 1; mat[1, 0] = 2; mat[2, 1] = 3; mat[2, 2] = 1
+    with pytest.raises(ValueError, match=r"Maximum matching possible only involves 2 out of 3 rows"):
+        sslap_b200.auction_solve(mat=mat)
+    with pytest.raises(ValueError, match="Fewer than 3 valid values provided for 3 rows"):
+        sslap_b200.auction_solve(loc=np.array([[0, 0], [1, 1]], dtype=np.int32), val=np.ones(2), size=(3, 3))
+    # unsorted COO: the kernel hands it on, the general path sorts it on the device
+    loc, val = make_problem(90, 0.2, "float", seed=9)
+    want = oracle_mod.auction_solve(loc=loc, val=val, problem="min")
+    order = np.lexsort((np.arange(len(val)), (loc[:, 0] * 7) % 13))            # rows regrouped, order inside a row kept
+    got = sslap_b200.auction_solve(loc=loc[order], val=val[order], size=(90, 90), problem="min", _raw_meta=True)
+    assert got["raw"].small_path == 0 and np.array_equal(got["sol"], want["sol"])
+    # the general path on the same small problems stays reachable
+    h.set_option("small_path", 0)
+    try:
+        got = sslap_b200.auction_solve(loc=loc, val=val, size=(90, 90), problem="min", _raw_meta=True)
+    finally:
+        h.set_option("small_path", 1)
+    assert got["raw"].small_path == 0 and np.array_equal(got["sol"], want["sol"])

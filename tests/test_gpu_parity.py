@@ -93,7 +93,11 @@ def test_bid_sweep_kernel_bit_exact(gpu, oracle_mod):
     L = nat.load()
     for (n, d, mode, seed) in [(1000, 0.01, "int", 3), (4000, 0.02, "float", 4), (257, 0.5, "int", 5)]:
         loc, val = make_problem(n, d, mode, seed=seed)
-        sslap_b200.auction_solve(loc=loc, val=val, size=(n, n), cardinality_check=False, max_iter=1)
+        h.set_option("small_path", 0)                     # the sweep needs the CSR resident on the handle
+        try:
+            sslap_b200.auction_solve(loc=loc, val=val, size=(n, n), cardinality_check=False, max_iter=1)
+        finally:
+            h.set_option("small_path", 1)
         rng = np.random.default_rng(seed)
         prices = rng.integers(0, 40, n).astype(np.float64) if mode == "int" else rng.uniform(0, 50, n)
         bidders = rng.permutation(n).astype(np.int32)[: max(1, n // 2)]
@@ -119,7 +123,11 @@ def test_bid_sweep_streamed_bit_exact(gpu, oracle_mod):
     for (n, d, mode, seed, m) in cases:
         loc, val = make_problem(n, d, mode, seed=seed, m=m)
         M = m or n
-        sslap_b200.auction_solve(loc=loc, val=val, size=(n, M), cardinality_check=False, max_iter=1)
+        h.set_option("small_path", 0)                     # the sweep needs the CSR resident on the handle
+        try:
+            sslap_b200.auction_solve(loc=loc, val=val, size=(n, M), cardinality_check=False, max_iter=1)
+        finally:
+            h.set_option("small_path", 1)
         rng = np.random.default_rng(seed)
         rowptr = np.searchsorted(loc[:, 0], np.arange(n + 1)).astype(np.int64)
         for kind in range(3):

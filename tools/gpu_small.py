@@ -16,13 +16,14 @@ try:
         ref = ref_loader.load()
 except Exception:
     pass
-for n in (10, 32, 100, 316):
+for n in (10, 20, 32, 48, 64, 100, 128, 200, 316):
     mat = make_matrix(n, 1.0, "float")
     tr = float("nan")
     if ref is not None:
         tr = min(_t for _t in [(lambda t0: (ref.auction_solve(mat.copy(), problem="max"), time.perf_counter() - t0)[1])(time.perf_counter()) for _ in range(10)])
-    for ctas in (0, 1, 2, 4, 16):
-        h.set_option("max_ctas", ctas)
+    h.set_option("small_max_n", 256)
+    for small in (1, 0):
+        h.set_option("small_path", small)
         for cc in (True, False):
             best, m = 1e9, None
             for _ in range(30):
@@ -31,6 +32,6 @@ for n in (10, 32, 100, 316):
                 dt = time.perf_counter() - t
                 if dt < best:
                     best, m = dt, r["raw"]
-            print(f"N={n:4d} max_ctas={ctas:3d} hk={int(cc)} wall {best*1e3:7.3f} ms (reference {tr*1e3:6.3f})  solve {m.solve_ms:6.3f} setup {m.setup_ms:6.3f} "
-                  f"hk {m.hk_ms:6.3f} h2d {m.h2d_ms:6.3f}  rounds g/w/s {m.rounds_grid}/{m.rounds_warp}/{m.rounds_solo}", flush=True)
-    h.set_option("max_ctas", 0)
+            print(f"N={n:4d} small_path={small} (taken {m.small_path}) hk={int(cc)} wall {best*1e3:7.3f} ms (reference {tr*1e3:6.3f})  solve {m.solve_ms:6.3f} setup {m.setup_ms:6.3f} "
+                  f"hk {m.hk_ms:6.3f} h2d {m.h2d_ms:6.3f}  its {m.its}", flush=True)
+    h.set_option("small_path", 1); h.set_option("small_max_n", 128)
