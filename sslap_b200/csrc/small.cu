@@ -422,11 +422,13 @@ extern "C" size_t sslapb_small_smem_bytes() { return sizeof(SmallShared); }
 
 extern "C" cudaError_t sslapb_launch_small(const SslapbSmallArgs *A, cudaStream_t stream)
 {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};                            // per device: the attribute belongs to the device's context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(sslapb_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     sslapb_small_kernel<<<1, SM_THREADS, sizeof(SmallShared), stream>>>(*A);
     return cudaGetLastError();
