@@ -729,19 +729,23 @@ static int run_small(sslapb_handle *h, const double *mat, const void *rows, cons
         CK(cudaMemcpyAsync(h->stage_val.p, val, (size_t)nnz * 8, cudaMemcpyHostToDevice, h->stream));
         A.val = h->stage_val.as<double>(); A.nnz = (int)nnz;
     }
-    CK(h->price.reserve((size_t)M * 8)); CK(h->p2o.reserve((size_t)N * 4)); CK(h->ctrl.reserve(sizeof(SslapbCtrl)));
-    static_assert(sizeof(SslapbSmallResult) <= sizeof(SslapbCtrl), "result block fits the control buffer");
+    // result block and `sol` side by side in one device buffer: ONE read-back
+    struct SmallOut { SslapbSmallResult res; int sol[SSLAPB_SMALL_MAXN]; };
+    CK(h->price.reserve((size_t)M * 8));
+    CK(h->ctrl.reserve(sizeof(SslapbCtrl) > sizeof(SmallOut) ? sizeof(SslapbCtrl) : sizeof(SmallOut)));
+    SmallOut *d_out = h->ctrl.as<SmallOut>();
     A.N = N; A.M = M; A.negate = !maximize; A.hk = cardinality_check ? 1 : 0; A.eps_start = eps_start; A.max_iter = max_iter;
-    A.sol_out = h->p2o.as<int>(); A.price_out = h->price.as<double>(); A.res = h->ctrl.as<SslapbSmallResult>();
+    A.sol_out = d_out->sol; A.price_out = h->price.as<double>(); A.res = &d_out->res;
     CK(cudaEventRecord(h->ev[1], h->stream));
     CK(sslapb_launch_small(&A, h->stream));
     CK(cudaEventRecord(h->ev[2], h->stream));
-    SslapbSmallResult R;
-    CK(cudaMemcpyAsync(&R, A.res, sizeof R, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(sol_out, A.sol_out, (size_t)N * 4, cudaMemcpyDeviceToHost, h->stream));
+    SmallOut out;
+    CK(cudaMemcpyAsync(&out, d_out, offsetof(SmallOut, sol) + (size_t)N * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    const SslapbSmallResult &R = out.res;
     if (R.status == 3) return SSLAPB_OK;                       // the general path takes it
     *handled = true;
+    if (R.status == 0) memcpy(sol_out, out.sol, (size_t)N * 4);
     h->N = N; h->M = M; h->nnz = R.nnz; h->has_vals = false; h->hot_valid = false;   // no resident CSR: prices only
     if (meta) {
         memset(meta, 0, sizeof *meta);
