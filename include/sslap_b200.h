@@ -102,8 +102,9 @@ int    sslapb_abi_version(void);
    "hk_host_loop" (1: Hopcroft-Karp phases driven from the host with one read-back per BFS level, as in round 1, instead of the
    device-resident loop; A/B runs; default 0),
    "batch_v1" (1: round 1's batch kernel — a whole warp sweeps one bidder at a time — instead of the sub-warp kernel; A/B runs),
-   "small_path" (0: never take the single-launch path for small problems — N, M <= 256 and <= 12288 entries, host buffers; tests
-   of the general path on small inputs; default 1),
+   "small_path" (0: never take the single-launch path for small problems — host buffers, default regime options, at most
+   12288 entries; tests of the general path on small inputs; default 1), "small_max_n" (largest N, M that take it: 1..256,
+   default 128),
    "hot" (0: never decide bids from the hot lists — A/B runs; default 1),
    "l2_persist" (1: persisting L2 access-policy window over the hot lists during a solve — A/B runs; measured no gain; default 0),
    "coop" (row-sharded solves only; 0: launch the persistent kernel without the cooperative attribute so that several of them
