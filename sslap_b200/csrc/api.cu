@@ -554,6 +554,11 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
     c.pmin_key[0] = 0x8000000000000000ull;                     // all prices start at +0.0 (auction_.pyx:220)
     c.pmin_key[1] = ~0ull;
     c.pmax_key = 0x8000000000000000ull;
+    // Exactness guard: the bound-pruned sweeps and the hot lists rest on prices never decreasing (bid = a - w + eps > p), i.e.
+    // on eps being large against the rounding of a price.  Where the smallest eps of the schedule comes within ~100 ulps of
+    // the cost magnitude (|a| * N beyond 1e14, or such an eps_start) every sweep reads and gathers the full row instead.
+    const bool tiny_eps = cmax * (double)N > 1e14 || (eps_start > 0 && (double)eps_start < cmax * 1e-13);
+    if (tiny_eps) c.pmax_key = 0xfff0000000000000ull;          // spread = +inf: no pruning
     CK(cudaMemcpyAsync(P.ctrl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
     if (warm) CK(sslapb_launch_price_bounds(&P, h->stream));   // pruning bounds of the first phase from the caller's prices
     int grid = h->grid;
@@ -563,7 +568,7 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
     if (h->max_ctas > 0 && h->max_ctas < grid) grid = h->max_ctas;
     // ---- hot lists (hot.cu): the 32 largest entries of every row + the bound of the rest
     bool l2_window = false;
-    if (h->hot && N > 32) {
+    if (h->hot && N > 32 && !tiny_eps) {
         size_t total = 0;
         char *hb = nullptr;
         rc = attach_hot_lists(h, P, &total, &hb);

@@ -261,6 +261,16 @@ def test_hot_lists_decide_bids_and_change_nothing(gpu, oracle_mod):
             assert np.array_equal(r["sol"], want["sol"]), (n, mode)
             assert_meta_equal(r["meta"], want["meta"])
             assert np.array_equal(r["prices"], want["prices"]), (n, mode)
+    # exactness guard: where the smallest eps comes within rounding distance of the prices (|a| * N > 1e14) neither the hot
+    # lists nor the bound pruning are used — and the trajectory is still the oracle's
+    loc, val = make_problem(600, 0.05, "float", seed=21)
+    val = val * 1e12
+    want = oracle_mod.auction_solve(loc=loc, val=val, problem="min", return_prices=True, max_iter=200000)
+    got = sslap_b200.auction_solve(loc=loc, val=val, size=(600, 600), problem="min", cardinality_check=False, _raw_meta=True,
+                                   return_prices=True, max_iter=200000)
+    assert got["raw"].hot_grid_bids == 0 and got["raw"].hot_tail_rounds == 0 and got["raw"].prune_second_pass == 0
+    assert np.array_equal(got["sol"], want["sol"]) and np.array_equal(got["prices"], want["prices"])
+    assert_meta_equal(got["meta"], want["meta"])
     rng = np.random.default_rng(5)
     mat = rng.uniform(0, 100, (1300, 1300))                                  # dense: rows of 1300 entries, the long-row instance
     want = oracle_mod.auction_solve(mat=mat, problem="max", return_prices=True)
