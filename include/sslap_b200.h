@@ -26,7 +26,7 @@ extern "C" {
 
 typedef struct sslapb_handle sslapb_handle;
 
-#define SSLAPB_ABI_VERSION 3      /* bumped whenever struct sslapb_meta or a prototype changes */
+#define SSLAPB_ABI_VERSION 4      /* bumped whenever struct sslapb_meta or a prototype changes */
 
 enum {
     SSLAPB_OK = 0,
@@ -66,7 +66,7 @@ typedef struct sslapb_meta {
     int64_t nnz;
     int64_t rounds_grid, rounds_warp, rounds_solo;   /* rounds executed per regime */
     float   prof_ms[8];      /* device time by section: grid bid, grid assign, grid compaction, warp regime, solo regime,
-                                eCE + phase change, (unused), grid barriers */
+                                eCE + phase change, mid regime, grid barriers */
     int64_t prune_second_pass; /* grid-regime rows whose bound-pruned sweep needed the second (exactness) gather pass */
     int32_t stop_reason;     /* 1 target-eps CS holds (:275) | 2 eps < target (:280) | 3 max_iter (:309) */
     int32_t small_path;      /* 1 when the single-launch path for small problems ran (small.cu); the field replaces round 1's
@@ -86,6 +86,8 @@ typedef struct sslapb_meta {
     int64_t hot_grid_bids, hot_grid_fallbacks;   /* grid-regime bids decided by the hot list / handed on to the full-row sweep */
     int64_t hot_tail_rounds, hot_tail_fallbacks; /* few-bidder + chain rounds run in hot form / their bids handed on to the full row */
     int64_t rounds_nohole;   /* rounds (of rounds_grid) that found no unowned object and no equal bids: no compaction, no final barrier */
+    /* ---- ABI version 4: mid regime (33..t_mid bidders in a hot-list phase: CTA 0 alone, block barriers; prof_ms[6] is its time) */
+    int64_t rounds_mid;      /* rounds executed by the mid regime; its = rounds_grid + rounds_mid + rounds_warp + rounds_solo */
 } sslapb_meta;
 
 int  sslapb_create(int device, sslapb_handle **out);
@@ -96,6 +98,8 @@ const char *sslapb_last_error(const sslapb_handle *h);
 size_t sslapb_meta_size(void);
 int    sslapb_abi_version(void);
 /* tuning knobs (none changes results): "t_small" (frontier size at or below which CTA 0 runs rounds alone, 0..32),
+   "t_mid" (mid regime: in eps-phases whose bids the hot lists decide, CTA 0 also runs the rounds of 33..t_mid bidders alone,
+   with block barriers instead of grid barriers; 0 = off, 33..256, default 128; only in effect with t_small = 32),
    "watchdog_ms" (device watchdog of a single barrier wait, default 120000),
    "t_shard" (row-sharded solves: rounds with more bidders than this are split over the ranks; default 16384),
    "max_ctas" (upper bound of the persistent kernel's grid, 0 = one CTA per SM; used to co-schedule several solves on one GPU),

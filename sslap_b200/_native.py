@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("SSLAP_B200_LIB", os.path.join(_HERE, "csrc", "libssla
 OK, E_FEWER_THAN_N, E_CARDINALITY, E_UNSORTED, E_BAD_ARG, E_OUT_OF_RANGE, E_EMPTY_ROW, E_ABORTED = range(8)
 MEM_HOST, MEM_DEVICE_IN, MEM_DEVICE_OUT = 0, 1, 2
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 COMM_EXPORT_BYTES, COMM_MAX_RANKS = 128, 8
 
 # every symbol include/sslap_b200.h declares (tests/test_abi.py checks this list against the header)
@@ -38,7 +38,8 @@ class Meta(C.Structure):
                 ("sweep_insitu_us", C.c_float), ("sweep_insitu_n", C.c_int32), ("warm_start", C.c_int32),
                 ("strict", C.c_int32),
                 ("hot_grid_bids", C.c_int64), ("hot_grid_fallbacks", C.c_int64),
-                ("hot_tail_rounds", C.c_int64), ("hot_tail_fallbacks", C.c_int64), ("rounds_nohole", C.c_int64)]
+                ("hot_tail_rounds", C.c_int64), ("hot_tail_fallbacks", C.c_int64), ("rounds_nohole", C.c_int64),
+                ("rounds_mid", C.c_int64)]
 
 
 _lib = None

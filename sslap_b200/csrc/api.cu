@@ -118,6 +118,7 @@ struct sslapb_handle {
     cudaEvent_t ev[6] = {};
     std::string err;
     int t_small = 32;
+    int t_mid = 128;               // mid regime: CTA 0 alone runs rounds of 33..t_mid bidders in hot-list phases (0: off; only with t_small == 32)
     long long watchdog_ms = 120000;
     int t_shard = 16384;           // row-sharded solves: rounds with more bidders than this are split over the ranks
     int max_ctas = 0;              // upper bound of the persistent kernel's grid (0: one CTA per SM)
@@ -238,6 +239,7 @@ extern "C" int sslapb_set_option(sslapb_handle *h, const char *name, int64_t val
     if (!h || !name) return SSLAPB_E_BAD_ARG;
     LOCK(h);
     if (!strcmp(name, "t_small")) { if (value < 0 || value > 32) return SSLAPB_E_BAD_ARG; h->t_small = (int)value; return 0; }
+    if (!strcmp(name, "t_mid")) { if (value != 0 && (value < 33 || value > 256)) return SSLAPB_E_BAD_ARG; h->t_mid = (int)value; return 0; }
     if (!strcmp(name, "watchdog_ms")) { if (value <= 0) return SSLAPB_E_BAD_ARG; h->watchdog_ms = value; return 0; }
     if (!strcmp(name, "t_shard")) { if (value < 0 || value > 0x7fffffff) return SSLAPB_E_BAD_ARG; h->t_shard = (int)value; return 0; }
     if (!strcmp(name, "max_ctas")) { if (value < 0 || value > 65535) return SSLAPB_E_BAD_ARG; h->max_ctas = (int)value; return 0; }
@@ -486,7 +488,7 @@ static int reserve_auction_state(sslapb_handle *h, SslapbAuctionParams &P)
     P.bidkey = h->bidkey.as<unsigned long long>(); P.winpos = h->winpos.as<int>();
     P.hole_count = h->hole_count.as<int>(); P.chosen = h->chosen.as<double>(); P.ctrl = h->ctrl.as<SslapbCtrl>();
     P.t_small = h->t_small;
-    P.cluster = 1; P.t_cluster = 0;                            // (unused fields)
+    P.t_mid = h->t_small == 32 ? h->t_mid : 0; P.pad_mid = 0;   // a caller that sets t_small is exercising the other regimes' hand-overs
     P.watchdog_ns = (unsigned long long)h->watchdog_ms * 1000000ull;
     P.nranks = 1; P.rank = 0; P.t_shard = 0x7fffffff; P.rowsplit = nullptr; P.xtab = nullptr; P.xcap = 0; P.xround_base = 0;
     return SSLAPB_OK;
@@ -663,6 +665,7 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
         meta->hot_grid_bids = c.hot_grid[0]; meta->hot_grid_fallbacks = c.hot_grid[1];
         meta->hot_tail_rounds = c.hot_tail[0]; meta->hot_tail_fallbacks = c.hot_tail[1];
         meta->rounds_nohole = c.rounds_nohole;
+        meta->rounds_mid = c.rounds_mid;
         (void)assigned;
     }
     return SSLAPB_OK;

@@ -1183,6 +1183,201 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
     if (fell && lane == 0) atomicAdd((unsigned long long *)&C->hot_tail[1], (unsigned long long)fell);
 }
 
+// ----------------------------------------------------------------------------------------------------------------------
+// Mid regime: 32 < nu <= t_mid (at most SSLAPB_MID) bidders in a phase whose bids the hot lists decide.  CTA 0 runs these
+// rounds alone with block barriers instead of grid barriers (a grid round of 33..128 bidders costs ~7.6 us at C3, of which
+// 3.4 us are barriers; 72 % of C3's grid rounds are of this size).  List positions are strided over the 16 warps (the next
+// position's hot row is requested before the current one is swept); merge: G = 512 / SSLAPB_MID... threads per position
+// scan the round's bids for a competitor on the same object (strict '>' at auction_.pyx:379: the earliest bidder in list
+// order keeps an equal bid); winners commit (:397-418), the evicted owner takes the winner's slot (:409) or leaves a hole
+// (:412); push_all_left (:137-162) only in rounds that produced a hole.  The list is double-buffered in shared memory and
+// handed to small_regime through P.list once nu <= 32.  Returns the new count; `its`, `done` are updated.
+// ----------------------------------------------------------------------------------------------------------------------
+#define SSLAPB_MID 256
+// sweep_hot<false> with the record gather taken out (the caller issues it — for the NEXT position before this one is
+// reduced — so that the gathers of a warp's positions overlap).  Same arithmetic, same exactness test.
+__device__ __forceinline__ bool sweep_hot_q(const SslapbHotRow &cur, const SslapbRec256 &q, double eps, SslapbBid &B)
+{
+    const double v = (cur.a - __longlong_as_double((long long)q.price_bits)) + 0.0;   // + 0.0 folds -0.0 into +0.0
+    const unsigned long long bk = sslapb_ord64(v);
+    const unsigned bh = (unsigned)(bk >> 32), bl = (unsigned)bk;
+    const unsigned khi = __reduce_max_sync(SSLAPB_FULL, bh);
+    if (khi <= (unsigned)(SSLAPB_KEY_NEG_INF >> 32)) return false;     // every candidate at -inf: the exact generic sweep decides
+    const unsigned hm = __ballot_sync(SSLAPB_FULL, bh == khi);
+    bool iswin;
+    unsigned own;
+    if ((hm & (hm - 1u)) == 0u) {                              // one lane holds the maximal high word: it is the winner
+        own = hm;
+        iswin = bh == khi;
+    } else {
+        const unsigned klo = __reduce_max_sync(SSLAPB_FULL, bh == khi ? bl : 0u);
+        const bool top = (bh == khi) & (bl == klo);
+        const int widx = __reduce_max_sync(SSLAPB_FULL, top ? cur.idx : -1);   // equal values: the later row entry wins (:351)
+        iswin = top & (cur.idx == widx);
+        own = __ballot_sync(SSLAPB_FULL, iswin);
+    }
+    int src;                                                   // the one lane of `own`
+    asm("bfind.u32 %0, %1;" : "=r"(src) : "r"(own));
+    const unsigned long long wo = __shfl_sync(SSLAPB_FULL, q.owner_deg, src);
+    B.pstart = (long long)__shfl_sync(SSLAPB_FULL, q.start, src);
+    B.powner = (int)(unsigned)wo;
+    B.pdeg = (int)(wo >> 32);
+    const unsigned long long cand = iswin ? 0ull : bk;         // one candidate per lane: second best = best of the other lanes
+    const unsigned chh = (unsigned)(cand >> 32), chl = (unsigned)cand;
+    const unsigned shi = __reduce_max_sync(SSLAPB_FULL, chh);
+    const unsigned slo = __reduce_max_sync(SSLAPB_FULL, chh == shi ? chl : 0u);
+    const unsigned long long skey = ((unsigned long long)shi << 32) | slo;
+    const double bc = __shfl_sync(SSLAPB_FULL, cur.a, src);
+    B.j = __shfl_sync(SSLAPB_FULL, cur.col, src);
+    const double wi = skey > SSLAPB_KEY_NEG_INF ? sslapb_key2double(skey) : SSLAPB_NEG_INF;   // :344
+    B.bid = (bc - wi) + eps;                                   // :360
+    return (wi > cur.rest) || (cur.rest == SSLAPB_NEG_INF);
+}
+// (inlined: after a call to an out-of-line mid_regime the compiler no longer takes the warps for converged, and every warp
+// collective of small_regime — the latency-bound few-bidder loops — gets a divergence check: 1.03 -> 1.14 us per round)
+#ifndef SSLAPB_MID_INLINE
+#define SSLAPB_MID_INLINE __forceinline__
+#endif
+#ifndef SSLAPB_MID_BATCH
+#define SSLAPB_MID_BATCH 4       // positions a warp keeps in flight (hot rows requested together, gathers software-pipelined)
+#endif
+#ifndef SSLAPB_KPARAM
+#define SSLAPB_KPARAM const __grid_constant__
+#endif
+static __device__ SSLAPB_MID_INLINE int mid_regime(const SslapbAuctionParams &Pk, SslapbCtrl *C, int nu, float eps_f, long long &its_io,
+                                                    long long max_iter, double pmin, double spread, int &done_out)
+{
+    long long its = its_io;
+    int done = 0;
+    nu = __shfl_sync(SSLAPB_FULL, nu, 0);                      // warp-uniform for the compiler (as is `warp` below)
+    SslapbAuctionParams P;                                     // out of line: the fields used below live in registers, not
+    P.hot = Pk.hot; P.rest = Pk.rest; P.rec = Pk.rec;          // behind a load from the kernel's parameter block per use
+    P.price = Pk.price; P.cols = Pk.cols; P.vals = Pk.vals; P.rowmax = Pk.rowmax;
+    __shared__ int m_li[2][SSLAPB_MID], m_dg[2][SSLAPB_MID];
+    __shared__ long long m_st[2][SSLAPB_MID];
+    __shared__ int m_j[SSLAPB_MID], m_po[SSLAPB_MID], m_pd[SSLAPB_MID];
+    __shared__ double m_bid[SSLAPB_MID];
+    __shared__ long long m_ps[SSLAPB_MID];
+    __shared__ unsigned m_hw[SSLAPB_MID / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(SSLAPB_FULL, tid >> 5, 0);
+    constexpr int NW = SSLAPB_THREADS / 32;
+    const double eps = (double)eps_f;
+    const unsigned long long t0 = sslapb_globaltimer();
+    long long rounds = 0;
+    int c = 0;                                                 // current half of the double-buffered list
+    if (tid < nu) {
+        const int v = Pk.list[tid];
+        const int li = v < -1 ? Pk.mover[-(v + 2)] : v;        // the grid regime leaves rank-encoded holes
+        const long long st = __ldg(Pk.rowptr + li);
+        m_li[0][tid] = li; m_st[0][tid] = st; m_dg[0][tid] = (int)(__ldg(Pk.rowptr + li + 1) - st);
+    }
+    __syncthreads();
+    while (nu > 32 && !done) {
+        // ---- bidding: warp w sweeps positions w, w + 16, ...; SSLAPB_MID_BATCH at a time: their hot rows are requested together, and the
+        // record gather of the next position is issued before the reduction of the current one
+        for (int a0 = warp; a0 < nu; a0 += SSLAPB_MID_BATCH * NW) {
+            SslapbHotRow row[SSLAPB_MID_BATCH];
+#pragma unroll
+            for (int k = 0; k < SSLAPB_MID_BATCH; ++k) {
+                const int a = a0 + k * NW;
+                row[k] = sslapb_load_hot(P, a < nu ? m_li[c][a] : 0, a < nu);   // beyond the list: padding row (column 0)
+            }
+            SslapbRec256 q = sslapb_ld_rec256(P.rec + row[0].col);
+            unsigned undecided = 0u;                           // positions the hot list could not decide (rare): swept below,
+#pragma unroll                                                 // out of the pipelined part (no call inside it)
+            for (int k = 0; k < SSLAPB_MID_BATCH; ++k) {
+                const int a = a0 + k * NW;
+                if (a >= nu) break;
+                SslapbRec256 qn = q;
+                if (k < SSLAPB_MID_BATCH - 1) qn = sslapb_ld_rec256(P.rec + row[k + 1].col);
+                SslapbBid b;
+                if (!sweep_hot_q(row[k], q, eps, b)) undecided |= 1u << k;
+                else if (lane == 0) { m_j[a] = b.j; m_bid[a] = b.bid; m_po[a] = b.powner; m_pd[a] = b.pdeg; m_ps[a] = b.pstart; }
+                q = qn;
+            }
+            while (undecided) {
+                const int a = a0 + (__ffs(undecided) - 1) * NW;
+                undecided &= undecided - 1u;
+                const long long st = m_st[c][a];
+                const SslapbBid b = row_bid_rec<32>(P.cols, P.vals, P.rec, st, st + m_dg[c][a], lane, eps, pmin,
+                                                    __ldg(P.rowmax + m_li[c][a]) - spread);
+                if (lane == 0) { m_j[a] = b.j; m_bid[a] = b.bid; m_po[a] = b.powner; m_pd[a] = b.pdeg; m_ps[a] = b.pstart; }
+            }
+        }
+        __syncthreads();
+        // ---- merge + assignment: 2 threads per position (4 when nu <= 128), each scans every 2nd (4th) bid
+        const int gs = nu <= SSLAPB_THREADS / 4 ? 2 : 1;       // log2(threads per position)
+        const int a = tid >> gs, q = tid & ((1 << gs) - 1);
+        const bool act = a < nu;
+        const int j = act ? m_j[a] : -1;
+        const double bid = act ? m_bid[a] : 0.0;
+        bool beaten = false;
+        if (j >= 0)
+            for (int s = q; s < nu; s += 1 << gs)
+                if (m_j[s] == j && s != a) {
+                    const double ob = m_bid[s];
+                    if (ob > bid || (ob == bid && s < a)) beaten = true;
+                }
+        const unsigned bb = __ballot_sync(SSLAPB_FULL, beaten);
+        const bool win = act && j >= 0 && ((bb >> (lane & ~((1 << gs) - 1))) & ((1u << (1 << gs)) - 1u)) == 0u;
+        bool hole = false;
+        if (act && q == 0) {
+            int nv = m_li[c][a], ndg = m_dg[c][a];
+            long long nst = m_st[c][a];
+            if (win) {
+                sslapb_st_rec256(P.rec + j, (unsigned long long)nst, ((unsigned long long)(unsigned)ndg << 32) | (unsigned)nv,
+                                 (unsigned long long)__double_as_longlong(bid));   // owner + its row (:418), price (:397)
+                P.price[j] = bid;
+                nv = m_po[a]; nst = m_ps[a]; ndg = m_pd[a];    // evicted owner takes the slot (:409) or hole (:412)
+            }
+            m_li[c ^ 1][a] = nv; m_st[c ^ 1][a] = nst; m_dg[c ^ 1][a] = ndg;
+            hole = nv < 0;
+        }
+        ++its; ++rounds;
+        if (__shfl_sync(SSLAPB_FULL, (int)(its >= max_iter), 0)) done = 3;
+        c ^= 1;
+        if (__syncthreads_or(hole)) {
+            // ---- push_all_left: the k-th hole left of the new count takes the k-th live entry right of it
+            const unsigned hb = __ballot_sync(SSLAPB_FULL, tid < nu && m_li[c][tid] < 0);
+            if (lane == 0 && warp < SSLAPB_MID / 32) m_hw[warp] = hb;
+            __syncthreads();
+            int nholes = 0;
+            for (int w = 0; w < SSLAPB_MID / 32; ++w) nholes += __popc(m_hw[w]);
+            const int new_nu = nu - nholes;                    // :429
+            int src = -1;
+            if (tid < new_nu && ((m_hw[warp] >> lane) & 1u)) {
+                int k = __popc(m_hw[warp] & ((1u << lane) - 1u));
+                for (int w = 0; w < warp; ++w) k += __popc(m_hw[w]);
+                for (int w = new_nu >> 5; w < SSLAPB_MID / 32; ++w) {
+                    const int lo = w << 5;
+                    const unsigned valid = nu >= lo + 32 ? SSLAPB_FULL : (nu <= lo ? 0u : (1u << (nu - lo)) - 1u);
+                    const unsigned right = new_nu <= lo ? SSLAPB_FULL : ~((1u << (new_nu - lo)) - 1u);
+                    unsigned m = valid & right & ~m_hw[w];
+                    const int cnt = __popc(m);
+                    if (k < cnt) {
+                        for (int r = 0; r < k; ++r) m &= m - 1u;   // drop the k lowest live entries
+                        src = lo + __ffs(m) - 1;
+                        break;
+                    }
+                    k -= cnt;
+                }
+            }
+            if (src >= 0) { m_li[c][tid] = m_li[c][src]; m_st[c][tid] = m_st[c][src]; m_dg[c][tid] = m_dg[c][src]; }
+            nu = __shfl_sync(SSLAPB_FULL, new_nu, 0);
+            __syncthreads();
+        }
+    }
+    if (tid < nu) Pk.list[tid] = m_li[c][tid];                 // small_regime (or the epilogue after max_iter) reads it there
+    if (tid == 0) {
+        C->rounds_mid += rounds;
+        C->prof[6] += sslapb_globaltimer() - t0;
+    }
+    __syncthreads();
+    its_io = its; done_out = done;
+    return nu;
+}
+
 // Block-wide exclusive prefix of a 0/1 flag over the threads of the CTA (in thread order); returns the CTA total in
 // `total`.  Uses warp ballots + one pass over the warp totals.
 __device__ __forceinline__ int block_excl_scan_flag(bool flag, int &total)
@@ -1586,7 +1781,7 @@ __device__ __forceinline__ void rebuild_p2o_owners(const SslapbAuctionParams &P,
 #ifdef SSLAPB_SHARDED
 #define sslapb_auction_kernel sslapb_auction_kernel_sharded   // row-sharded multi-GPU instance, see auction_sharded.cu
 #endif
-__global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(SslapbAuctionParams P)
+__global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(SSLAPB_KPARAM SslapbAuctionParams P)
 {
     SslapbCtrl *C = P.ctrl;
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(SSLAPB_FULL, tid >> 5, 0);
@@ -1633,7 +1828,11 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
         __syncthreads();                                       // s_top is rewritten only after every thread has read it
         if (done) break;
 
-        if (nu > P.t_small) {
+        // mid regime (CTA 0 alone, block barriers) only in phases whose bids the hot lists decide: a bid is then one 512-byte
+        // row + one record gather, and 16 warps finish a round of up to t_mid bidders before three grid barriers would
+        const bool hot_small = hot_mode && P.hot != nullptr;
+        const int t_lim = (hot_small && P.t_mid > P.t_small) ? P.t_mid : P.t_small;
+        if (nu > t_lim) {
             // ================================ grid regime: one round ================================
             const SslapbScope S = {(int)blockIdx.x, (int)nblk, gwarp, nwarps, gtid == 0};
             long long its_l = its;
@@ -1645,7 +1844,16 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(Sslap
             }
         } else {
             // ================================ warp-list regimes: CTA 0 finishes the phase ================================
-            if (blockIdx.x == 0) small_regime(P, C, nu, eps_f, its, max_iter, pmin, spread, hot_mode && P.hot != nullptr);
+            if (blockIdx.x == 0) {
+                int nu_l = nu, done_l = 0;
+                long long its_l = its;
+                if (nu > 32) nu_l = mid_regime(P, C, nu, eps_f, its_l, max_iter, pmin, spread, done_l);
+                // shuffles: warp-uniform for the compiler (otherwise every warp collective of small_regime gets a divergence
+                // check: +5 % instructions in the few-bidder loops, 1.03 -> 1.14 us per round measured)
+                nu_l = __shfl_sync(SSLAPB_FULL, nu_l, 0); done_l = __shfl_sync(SSLAPB_FULL, done_l, 0);
+                if (!done_l) small_regime(P, C, nu_l, eps_f, its_l, max_iter, pmin, spread, hot_small);
+                else if (tid == 0) { C->nu = nu_l; C->its = its_l; C->done = done_l; }   // max_iter inside the mid regime
+            }
             GB();
         }
 

@@ -23,7 +23,7 @@ struct SslapbCtrl {
     int tie_flag;             // some atomicMax saw an equal bid this round -> run the position tie-break pass
     int ece_final;            // meta['eCE'] (:297); -1 until known
     long long rounds_grid, rounds_warp, rounds_solo;   // instrumentation: rounds executed per regime
-    long long rounds_cluster;                          // (unused: round 1's cluster regime was removed)
+    long long rounds_mid;                              // rounds of the mid regime (CTA 0 alone, 33..t_mid bidders, hot phases)
     unsigned long long pmin_key[2];                    // order-preserving image of a LOWER bound of every price (slot = phase & 1);
                                                        // prices never decrease, so a phase-start minimum stays valid all phase
     unsigned long long pmax_key;                       // running maximum of the prices (atomicMax by every winner): heuristic only
@@ -32,7 +32,7 @@ struct SslapbCtrl {
     unsigned dbg[16];                                  // (unused)
                                                        // ((round << 3) | barrier index), reported when the watchdog fires
     unsigned long long prof[8];                        // ns spent (CTA 0 view): 0 grid bid, 1 grid tie+assign, 2 grid compaction,
-                                                       // 3 warp regime, 4 solo regime, 5 eCE/phase change, 6 (unused), 7 barriers of the grid regime
+                                                       // 3 warp regime, 4 solo regime, 5 eCE/phase change, 6 mid regime, 7 barriers of the grid regime
     long long rounds_sharded;                          // row-sharded solve: rounds whose bidding was split over the ranks
     unsigned long long xchg_ns;                        // ... ns CTA 0 spent in their cross-GPU exchange barrier (signal + wait)
     unsigned long long sharded_ns;                     // ... ns of those rounds in total (CTA 0 view)
@@ -88,7 +88,8 @@ struct SslapbAuctionParams {
     double *chosen;           // per person: sum of (folded) values of entries equal to its object (get_obj, :504-521)
     SslapbCtrl *ctrl;
     int t_small;              // nu <= t_small (<= 32) -> CTA 0 runs the round alone (warp-list regime)
-    int t_cluster, cluster;   // (unused: round 1's cluster regime was removed; kept so that the layout is unchanged)
+    int t_mid;                // 32 < nu <= t_mid in a hot-list phase -> CTA 0 runs the round alone (mid regime); 0 = off
+    int pad_mid;
     unsigned long long watchdog_ns;
     // ---- row-sharded solve over several GPUs (instance of auction_sharded.cu; nranks == 1: off).  Persons are split into
     // nnz-balanced contiguous row ranges; every rank holds the whole state and CSR, but in rounds with nu > t_shard it sweeps

@@ -249,14 +249,15 @@ def test_hot_lists_decide_bids_and_change_nothing(gpu, oracle_mod):
         raw = got["raw"]
         assert raw.hot_grid_bids > 0 and raw.hot_tail_rounds > 0, (n, raw.hot_grid_bids, raw.hot_tail_rounds)
         assert raw.hot_grid_fallbacks > 0                                    # the first phase has no bounds yet: all handed on
-        assert 0 < raw.rounds_nohole <= raw.rounds_grid
+        assert 0 <= raw.rounds_nohole <= raw.rounds_grid                     # (small frontiers: the mid regime takes them)
         h.set_option("hot", 0)
         try:
             off = sslap_b200.auction_solve(loc=loc, val=val, size=(n, n), problem="min", cardinality_check=False,
                                            _raw_meta=True, return_prices=True)
         finally:
             h.set_option("hot", 1)
-        assert off["raw"].hot_grid_bids == 0 and off["raw"].hot_tail_rounds == 0
+        assert off["raw"].hot_grid_bids == 0 and off["raw"].hot_tail_rounds == 0 and off["raw"].rounds_mid == 0
+        assert 0 < off["raw"].rounds_nohole <= off["raw"].rounds_grid
         for r in (got, off):
             assert np.array_equal(r["sol"], want["sol"]), (n, mode)
             assert_meta_equal(r["meta"], want["meta"])
@@ -278,6 +279,54 @@ def test_hot_lists_decide_bids_and_change_nothing(gpu, oracle_mod):
     assert got["raw"].hot_tail_rounds > 0
     assert np.array_equal(got["sol"], want["sol"]) and np.array_equal(got["prices"], want["prices"])
     assert_meta_equal(got["meta"], want["meta"])
+
+
+def test_mid_regime_runs_and_changes_nothing(gpu, oracle_mod):
+    """Mid regime (auction.cu mid_regime): in eps-phases whose bids the hot lists decide, CTA 0 runs the rounds of
+    33..t_mid bidders alone.  It must run at the default threshold, and sol / meta / float64 prices must equal the oracle's
+    bit for bit at every threshold (off, just above the warp regimes, default, maximum) — float costs, integer costs and
+    heavily tied costs (equal bids: the earliest bidder in list order wins, auction_.pyx:379), a rectangular instance
+    (holes and push_all_left, :137-162), and iteration caps that end the solve inside a mid-regime round."""
+    sslap_b200, nat, h = gpu
+    cases = [(4000, 4000, 0.02, "float", 31, False), (3000, 3000, 0.03, "int", 32, False), (2500, 2500, 0.04, "int", 33, True),
+             (2000, 2300, 0.03, "float", 34, False), (6000, 6000, 0.01, "float", 35, True)]
+    for (n, m, d, mode, seed, tied) in cases:
+        loc, val = make_problem(n, d, mode, seed=seed, m=m)
+        if tied:
+            val = np.round(val / 10.0)
+        want = oracle_mod.auction_solve(loc=loc, val=val, problem="max", return_prices=True)
+        mids = {}
+        for t_mid in (0, 33, 128, 256):
+            h.set_option("t_mid", t_mid)
+            try:
+                got = sslap_b200.auction_solve(loc=loc, val=val, size=(n, m), problem="max", cardinality_check=False,
+                                               _raw_meta=True, return_prices=True)
+            finally:
+                h.set_option("t_mid", 128)
+            raw = got["raw"]
+            mids[t_mid] = int(raw.rounds_mid)
+            assert raw.rounds_grid + raw.rounds_mid + raw.rounds_warp + raw.rounds_solo == raw.its, (n, t_mid)
+            assert np.array_equal(got["sol"], want["sol"]), (n, mode, tied, t_mid)
+            assert_meta_equal(got["meta"], want["meta"])
+            assert np.array_equal(got["prices"], want["prices"]), (n, mode, tied, t_mid)
+        assert mids[0] == 0, (n, mids)
+        assert mids[128] > 0 or tied or n != m, (n, mids)        # (tied costs rarely let a hot list prove its answer)
+    # iteration caps spread over the whole solve: some end inside a mid-regime round (the list goes back to global memory)
+    loc, val = make_problem(3000, 0.03, "float", seed=36)
+    full = oracle_mod.auction_solve(loc=loc, val=val, problem="min")
+    its = int(full["meta"]["its"])
+    hit = 0
+    for cap in sorted({max(1, its * k // 40) for k in range(1, 40)}):
+        want = oracle_mod.auction_solve(loc=loc, val=val, problem="min", max_iter=cap)
+        got = sslap_b200.auction_solve(loc=loc, val=val, size=(3000, 3000), problem="min", cardinality_check=False,
+                                       max_iter=cap, _raw_meta=True)
+        assert np.array_equal(got["sol"], want["sol"]), cap
+        assert_meta_equal(got["meta"], want["meta"])
+        hit += int(got["raw"].rounds_mid > 0)
+    assert hit > 0
+    for bad in (1, 32, 257, -3):
+        with pytest.raises(ValueError):
+            h.set_option("t_mid", bad)
 
 
 @pytest.mark.parametrize("k_ranks", [2, 4, 8])
