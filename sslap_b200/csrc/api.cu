@@ -118,7 +118,7 @@ struct sslapb_handle {
     cudaEvent_t ev[6] = {};
     std::string err;
     int t_small = 32;
-    int t_mid = 128;               // mid regime: CTA 0 alone runs rounds of 33..t_mid bidders in hot-list phases (0: off; only with t_small == 32)
+    int t_mid = SSLAPB_MID < 128 ? SSLAPB_MID : 128;               // mid regime: CTA 0 alone runs rounds of 33..t_mid bidders in hot-list phases (0: off; only with t_small == 32)
     long long watchdog_ms = 120000;
     int t_shard = 16384;           // row-sharded solves: rounds with more bidders than this are split over the ranks
     int max_ctas = 0;              // upper bound of the persistent kernel's grid (0: one CTA per SM)
@@ -239,7 +239,7 @@ extern "C" int sslapb_set_option(sslapb_handle *h, const char *name, int64_t val
     if (!h || !name) return SSLAPB_E_BAD_ARG;
     LOCK(h);
     if (!strcmp(name, "t_small")) { if (value < 0 || value > 32) return SSLAPB_E_BAD_ARG; h->t_small = (int)value; return 0; }
-    if (!strcmp(name, "t_mid")) { if (value != 0 && (value < 33 || value > 256)) return SSLAPB_E_BAD_ARG; h->t_mid = (int)value; return 0; }
+    if (!strcmp(name, "t_mid")) { if (value != 0 && (value < 33 || value > SSLAPB_MID)) return SSLAPB_E_BAD_ARG; h->t_mid = (int)value; return 0; }
     if (!strcmp(name, "watchdog_ms")) { if (value <= 0) return SSLAPB_E_BAD_ARG; h->watchdog_ms = value; return 0; }
     if (!strcmp(name, "t_shard")) { if (value < 0 || value > 0x7fffffff) return SSLAPB_E_BAD_ARG; h->t_shard = (int)value; return 0; }
     if (!strcmp(name, "max_ctas")) { if (value < 0 || value > 65535) return SSLAPB_E_BAD_ARG; h->max_ctas = (int)value; return 0; }

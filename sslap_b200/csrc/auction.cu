@@ -1191,9 +1191,8 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
 // scan the round's bids for a competitor on the same object (strict '>' at auction_.pyx:379: the earliest bidder in list
 // order keeps an equal bid); winners commit (:397-418), the evicted owner takes the winner's slot (:409) or leaves a hole
 // (:412); push_all_left (:137-162) only in rounds that produced a hole.  The list is double-buffered in shared memory and
-// handed to small_regime through P.list once nu <= 32.  Returns the new count; `its`, `done` are updated.
+// handed to small_regime through P.list (and the control block) once nu <= 32.
 // ----------------------------------------------------------------------------------------------------------------------
-#define SSLAPB_MID 256
 // sweep_hot<false> with the record gather taken out (the caller issues it — for the NEXT position before this one is
 // reduced — so that the gathers of a warp's positions overlap).  Same arithmetic, same exactness test.
 __device__ __forceinline__ bool sweep_hot_q(const SslapbHotRow &cur, const SslapbRec256 &q, double eps, SslapbBid &B)
@@ -1244,10 +1243,9 @@ __device__ __forceinline__ bool sweep_hot_q(const SslapbHotRow &cur, const Sslap
 #ifndef SSLAPB_KPARAM
 #define SSLAPB_KPARAM const __grid_constant__
 #endif
-static __device__ SSLAPB_MID_INLINE int mid_regime(const SslapbAuctionParams &Pk, SslapbCtrl *C, int nu, float eps_f, long long &its_io,
-                                                    long long max_iter, double pmin, double spread, int &done_out)
+static __device__ SSLAPB_MID_INLINE void mid_regime(const SslapbAuctionParams &Pk, SslapbCtrl *C, int nu, float eps_f, long long its,
+                                                     long long max_iter, double pmin, double spread)
 {
-    long long its = its_io;
     int done = 0;
     nu = __shfl_sync(SSLAPB_FULL, nu, 0);                      // warp-uniform for the compiler (as is `warp` below)
     SslapbAuctionParams P;                                     // out of line: the fields used below live in registers, not
@@ -1370,12 +1368,12 @@ static __device__ SSLAPB_MID_INLINE int mid_regime(const SslapbAuctionParams &Pk
     }
     if (tid < nu) Pk.list[tid] = m_li[c][tid];                 // small_regime (or the epilogue after max_iter) reads it there
     if (tid == 0) {
+        C->nu = nu;
+        C->its = its;
+        if (done) C->done = done;
         C->rounds_mid += rounds;
         C->prof[6] += sslapb_globaltimer() - t0;
     }
-    __syncthreads();
-    its_io = its; done_out = done;
-    return nu;
 }
 
 // Block-wide exclusive prefix of a 0/1 flag over the threads of the CTA (in thread order); returns the CTA total in
@@ -1842,18 +1840,16 @@ __global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(SSLAP
                 if (r == 1) break;
                 ++its_l;                                       // r == 2: same frontier, next round straight away
             }
-        } else {
+        } else if (nu <= 32) {
             // ================================ warp-list regimes: CTA 0 finishes the phase ================================
-            if (blockIdx.x == 0) {
-                int nu_l = nu, done_l = 0;
-                long long its_l = its;
-                if (nu > 32) nu_l = mid_regime(P, C, nu, eps_f, its_l, max_iter, pmin, spread, done_l);
-                // shuffles: warp-uniform for the compiler (otherwise every warp collective of small_regime gets a divergence
-                // check: +5 % instructions in the few-bidder loops, 1.03 -> 1.14 us per round measured)
-                nu_l = __shfl_sync(SSLAPB_FULL, nu_l, 0); done_l = __shfl_sync(SSLAPB_FULL, done_l, 0);
-                if (!done_l) small_regime(P, C, nu_l, eps_f, its_l, max_iter, pmin, spread, hot_small);
-                else if (tid == 0) { C->nu = nu_l; C->its = its_l; C->done = done_l; }   // max_iter inside the mid regime
-            }
+            if (blockIdx.x == 0) small_regime(P, C, nu, eps_f, its, max_iter, pmin, spread, hot_small);
+            GB();
+        } else {
+            // ================================ mid regime: CTA 0 runs rounds until nu <= 32 ================================
+            // (the LAST branch of the chain, so that its code lies behind small_regime's in the binary, with its own barrier
+            // and a trip through the loop top before small_regime takes over: the few-bidder loops are sensitive to the code
+            // around their call site and to their placement)
+            if (blockIdx.x == 0) mid_regime(P, C, nu, eps_f, its, max_iter, pmin, spread);
             GB();
         }
 

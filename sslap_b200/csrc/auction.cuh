@@ -102,4 +102,7 @@ struct SslapbAuctionParams {
     unsigned xround_base;     // sharded rounds completed by earlier solves on this communicator (flags are monotone)
 };
 
+#ifndef SSLAPB_MID
+#define SSLAPB_MID 256           // capacity (bidders) of the mid regime's shared-memory list; option "t_mid" is at most this
+#endif
 #define SSLAPB_MAX_RANKS 8

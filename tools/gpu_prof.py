@@ -42,9 +42,17 @@ if which == "midsweep":                                      # the mid regime's 
         try:
             h.set_option("t_mid", t_mid)
         except Exception as e:
-            print("t_mid not settable:", e); run("C3", 100000, 0.001, reps=2); break
+            if "unknown option" in str(e):
+                print("t_mid not settable:", e); run("C3", 100000, 0.001, reps=2); break
+            continue                                         # a build with a smaller SSLAPB_MID
         run(f"C3 t_mid={t_mid}", 100000, 0.001, reps=2)
-        run(f"C2 t_mid={t_mid}", 10000, 0.01, reps=2)
+        if os.environ.get("PROF_C2"): run(f"C2 t_mid={t_mid}", 10000, 0.01, reps=2)
+if which == "c3mid0":                                        # C3 with the mid regime off (code-placement A/B of the other loops)
+    try:
+        h.set_option("t_mid", 0)
+    except Exception:
+        pass
+    run("C3 t_mid=0", 100000, 0.001, reps=2)
 if which == "c3only":
     run("C3", 100000, 0.001, reps=3)
 if which in ("c3", "both"):
