@@ -1237,6 +1237,9 @@ __device__ __forceinline__ bool sweep_hot_q(const SslapbHotRow &cur, const Sslap
 #ifndef SSLAPB_MID_INLINE
 #define SSLAPB_MID_INLINE __forceinline__
 #endif
+#ifndef SSLAPB_MID_PROF
+#define SSLAPB_MID_PROF 0
+#endif
 #ifndef SSLAPB_MID_BATCH
 #define SSLAPB_MID_BATCH 4       // positions a warp keeps in flight (hot rows requested together, gathers software-pipelined)
 #endif
@@ -1253,7 +1256,8 @@ static __device__ SSLAPB_MID_INLINE void mid_regime(const SslapbAuctionParams &P
     P.price = Pk.price; P.cols = Pk.cols; P.vals = Pk.vals; P.rowmax = Pk.rowmax;
     __shared__ int m_li[2][SSLAPB_MID], m_dg[2][SSLAPB_MID];
     __shared__ long long m_st[2][SSLAPB_MID];
-    __shared__ int m_j[SSLAPB_MID], m_po[SSLAPB_MID], m_pd[SSLAPB_MID];
+    __shared__ __align__(16) int m_j[SSLAPB_MID];
+    __shared__ int m_po[SSLAPB_MID], m_pd[SSLAPB_MID];
     __shared__ double m_bid[SSLAPB_MID];
     __shared__ long long m_ps[SSLAPB_MID];
     __shared__ unsigned m_hw[SSLAPB_MID / 32];
@@ -1271,7 +1275,15 @@ static __device__ SSLAPB_MID_INLINE void mid_regime(const SslapbAuctionParams &P
         m_li[0][tid] = li; m_st[0][tid] = st; m_dg[0][tid] = (int)(__ldg(Pk.rowptr + li + 1) - st);
     }
     __syncthreads();
+#if SSLAPB_MID_PROF
+    unsigned long long tacc = 0, ts = 0;                       // profiling builds: prof[6] = 1 bidding / 2 merge / 3 compaction part only
+#endif
     while (nu > 32 && !done) {
+#if SSLAPB_MID_PROF == 1
+        ts = sslapb_globaltimer();
+#elif SSLAPB_MID_PROF == 4
+        tacc += nu;                                            // (+ bids / 1e6 in the same figure)
+#endif
         // ---- bidding: warp w sweeps positions w, w + 16, ...; SSLAPB_MID_BATCH at a time: their hot rows are requested together, and the
         // record gather of the next position is issued before the reduction of the current one
         for (int a0 = warp; a0 < nu; a0 += SSLAPB_MID_BATCH * NW) {
@@ -1291,9 +1303,18 @@ static __device__ SSLAPB_MID_INLINE void mid_regime(const SslapbAuctionParams &P
                 if (k < SSLAPB_MID_BATCH - 1) qn = sslapb_ld_rec256(P.rec + row[k + 1].col);
                 SslapbBid b;
                 if (!sweep_hot_q(row[k], q, eps, b)) undecided |= 1u << k;
-                else if (lane == 0) { m_j[a] = b.j; m_bid[a] = b.bid; m_po[a] = b.powner; m_pd[a] = b.pdeg; m_ps[a] = b.pstart; }
+                else {
+                    if (lane == 0) { m_j[a] = b.j; m_bid[a] = b.bid; m_po[a] = b.powner; m_pd[a] = b.pdeg; m_ps[a] = b.pstart; }
+                    // the owner takes this position when the bid wins: its hot row (4 lines) is on its way for the next round
+                    if (lane < 4 && b.powner >= 0)
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char *>(P.hot) +
+                                                                         ((unsigned long long)(unsigned)b.powner << 9) + (lane << 7)));
+                }
                 q = qn;
             }
+#if SSLAPB_MID_PROF == 4
+            if (lane == 0 && undecided) atomicAdd(&C->prof[6], 1000ull * __popc(undecided));   // prof_ms[6] * 1000 = undecided bids
+#endif
             while (undecided) {
                 const int a = a0 + (__ffs(undecided) - 1) * NW;
                 undecided &= undecided - 1u;
@@ -1304,6 +1325,11 @@ static __device__ SSLAPB_MID_INLINE void mid_regime(const SslapbAuctionParams &P
             }
         }
         __syncthreads();
+#if SSLAPB_MID_PROF == 1
+        tacc += sslapb_globaltimer() - ts;
+#elif SSLAPB_MID_PROF == 2
+        ts = sslapb_globaltimer();
+#endif
         // ---- merge + assignment: 2 threads per position (4 when nu <= 128), each scans every 2nd (4th) bid
         const int gs = nu <= SSLAPB_THREADS / 4 ? 2 : 1;       // log2(threads per position)
         const int a = tid >> gs, q = tid & ((1 << gs) - 1);
@@ -1311,12 +1337,17 @@ static __device__ SSLAPB_MID_INLINE void mid_regime(const SslapbAuctionParams &P
         const int j = act ? m_j[a] : -1;
         const double bid = act ? m_bid[a] : 0.0;
         bool beaten = false;
-        if (j >= 0)
-            for (int s = q; s < nu; s += 1 << gs)
-                if (m_j[s] == j && s != a) {
-                    const double ob = m_bid[s];
-                    if (ob > bid || (ob == bid && s < a)) beaten = true;
-                }
+        if (j >= 0) {
+            // four positions per shared-memory load; entries at or beyond nu are stale (excluded in `other`)
+            auto other = [&](int s) { const double ob = m_bid[s]; return s != a && s < nu && (ob > bid || (ob == bid && s < a)); };
+            for (int ch = q; ch * 4 < nu; ch += 1 << gs) {
+                const int4 v = reinterpret_cast<const int4 *>(m_j)[ch];
+                if (v.x == j && other(4 * ch)) beaten = true;
+                if (v.y == j && other(4 * ch + 1)) beaten = true;
+                if (v.z == j && other(4 * ch + 2)) beaten = true;
+                if (v.w == j && other(4 * ch + 3)) beaten = true;
+            }
+        }
         const unsigned bb = __ballot_sync(SSLAPB_FULL, beaten);
         const bool win = act && j >= 0 && ((bb >> (lane & ~((1 << gs) - 1))) & ((1u << (1 << gs)) - 1u)) == 0u;
         bool hole = false;
@@ -1335,7 +1366,13 @@ static __device__ SSLAPB_MID_INLINE void mid_regime(const SslapbAuctionParams &P
         ++its; ++rounds;
         if (__shfl_sync(SSLAPB_FULL, (int)(its >= max_iter), 0)) done = 3;
         c ^= 1;
-        if (__syncthreads_or(hole)) {
+        const int any_hole = __syncthreads_or(hole);
+#if SSLAPB_MID_PROF == 2
+        tacc += sslapb_globaltimer() - ts;
+#elif SSLAPB_MID_PROF == 3
+        ts = sslapb_globaltimer();
+#endif
+        if (any_hole) {
             // ---- push_all_left: the k-th hole left of the new count takes the k-th live entry right of it
             const unsigned hb = __ballot_sync(SSLAPB_FULL, tid < nu && m_li[c][tid] < 0);
             if (lane == 0 && warp < SSLAPB_MID / 32) m_hw[warp] = hb;
@@ -1365,6 +1402,9 @@ static __device__ SSLAPB_MID_INLINE void mid_regime(const SslapbAuctionParams &P
             nu = __shfl_sync(SSLAPB_FULL, new_nu, 0);
             __syncthreads();
         }
+#if SSLAPB_MID_PROF == 3
+        tacc += sslapb_globaltimer() - ts;
+#endif
     }
     if (tid < nu) Pk.list[tid] = m_li[c][tid];                 // small_regime (or the epilogue after max_iter) reads it there
     if (tid == 0) {
@@ -1372,7 +1412,11 @@ static __device__ SSLAPB_MID_INLINE void mid_regime(const SslapbAuctionParams &P
         C->its = its;
         if (done) C->done = done;
         C->rounds_mid += rounds;
+#if SSLAPB_MID_PROF
+        C->prof[6] += tacc;
+#else
         C->prof[6] += sslapb_globaltimer() - t0;
+#endif
     }
 }
 

@@ -54,7 +54,7 @@ if which == "c3mid0":                                        # C3 with the mid r
         pass
     run("C3 t_mid=0", 100000, 0.001, reps=2)
 if which == "c3only":
-    run("C3", 100000, 0.001, reps=3)
+    run("C3", 100000, 0.001, reps=2)
 if which in ("c3", "both"):
     loc, val = run("C3", 100000, 0.001)
     h.set_option("hot", 0); run("C3 hot off", 100000, 0.001, reps=1); h.set_option("hot", 1)
