@@ -352,7 +352,8 @@ def main():
             "result": {"its": its, "objective": obj},
             "solve_s": ms_step * 1e-3,
             "device_ms": {"csr_build": float(np.mean(setup_ms)), "auction_kernel": float(np.mean(solve_ms)),
-                          "rounds": {"grid": int(meta.rounds_grid), "warp": int(meta.rounds_warp), "chain": int(meta.rounds_solo)},
+                          "rounds": {"grid": int(meta.rounds_grid), "mid": int(meta.rounds_mid), "warp": int(meta.rounds_warp),
+                                     "chain": int(meta.rounds_solo)},
                           "sections_ms": [round(float(x), 3) for x in meta.prof_ms], "hot_lists": hot_stats},
             "e2e": {"value": nnz / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(loc.nbytes + val.nbytes) * world,

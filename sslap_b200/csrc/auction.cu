@@ -14,6 +14,8 @@
 //   grid      (nu > t_small = 32): all CTAs; warp per bidder; 64-bit atomicMax of the order-preserving bid per object
 //                                  (+ an atomicMin of the list position only in rounds where an equal bid was seen);
 //                                  3 grid barriers (spread_round).
+//   33..t_mid CTA 0 only, in eps-phases whose bids the hot lists decide (t_mid = 128): positions strided over its 16 warps
+//             with pipelined record gathers, merge by all 512 threads, block barriers instead of grid barriers (mid_regime).
 //   17..32    CTA 0 only; list positions strided over its 16 warps, warp 0 merges through shuffles (warp_resolve).
 //   3..16     CTA 0 only; warp a owns position a; ONE named barrier per round, outcome derived redundantly in registers
 //             (multi_rounds; the instance of auction_long.cu keeps a two-barrier form with a whole-CTA sweep of very
@@ -1186,12 +1188,18 @@ __device__ __forceinline__ void small_regime(const SslapbAuctionParams &P, Sslap
 // ----------------------------------------------------------------------------------------------------------------------
 // Mid regime: 32 < nu <= t_mid (at most SSLAPB_MID) bidders in a phase whose bids the hot lists decide.  CTA 0 runs these
 // rounds alone with block barriers instead of grid barriers (a grid round of 33..128 bidders costs ~7.6 us at C3, of which
-// 3.4 us are barriers; 72 % of C3's grid rounds are of this size).  List positions are strided over the 16 warps (the next
-// position's hot row is requested before the current one is swept); merge: G = 512 / SSLAPB_MID... threads per position
-// scan the round's bids for a competitor on the same object (strict '>' at auction_.pyx:379: the earliest bidder in list
-// order keeps an equal bid); winners commit (:397-418), the evicted owner takes the winner's slot (:409) or leaves a hole
-// (:412); push_all_left (:137-162) only in rounds that produced a hole.  The list is double-buffered in shared memory and
-// handed to small_regime through P.list (and the control block) once nu <= 32.
+// 3.4 us are barriers; 72 % of C3's grid rounds are of this size).
+//   bidding   list positions strided over the 16 warps, SSLAPB_MID_BATCH positions of a warp in flight: their hot rows
+//             are requested together and the record gather of the next position is issued before the reduction of the
+//             current one (sweep_hot_q); the rare bid a hot list cannot decide takes the exact full-row sweep afterwards;
+//             a decided bid prefetches the hot row of the object's owner, who takes the position if the bid wins;
+//   merge     2 threads per position (4 when nu <= 128) scan the round's bids, four per shared-memory load, for a
+//             competitor on the same object (strict '>' at auction_.pyx:379: the earliest bidder in list order keeps an
+//             equal bid); winners commit (:397-418), the evicted owner takes the winner's slot (:409) or leaves a hole (:412);
+//   compaction push_all_left (:137-162) by ballot words, only in rounds that produced a hole (15 % at C3).
+// The list is double-buffered in shared memory and handed to small_regime through P.list and the control block once
+// nu <= 32.  Measured at C3 (profiles/r2_mid_regime_ab.log, -DSSLAPB_MID_PROF builds): 3,898 rounds at 3.65 us — bidding
+// 2.1, merge 1.4, compaction 0.1 — against 7.6 us in the grid regime; the solve 199.6 -> 185.4 ms on the same box.
 // ----------------------------------------------------------------------------------------------------------------------
 // sweep_hot<false> with the record gather taken out (the caller issues it — for the NEXT position before this one is
 // reduced — so that the gathers of a warp's positions overlap).  Same arithmetic, same exactness test.
@@ -1232,27 +1240,23 @@ __device__ __forceinline__ bool sweep_hot_q(const SslapbHotRow &cur, const Sslap
     B.bid = (bc - wi) + eps;                                   // :360
     return (wi > cur.rest) || (cur.rest == SSLAPB_NEG_INF);
 }
-// (inlined: after a call to an out-of-line mid_regime the compiler no longer takes the warps for converged, and every warp
-// collective of small_regime — the latency-bound few-bidder loops — gets a divergence check: 1.03 -> 1.14 us per round)
-#ifndef SSLAPB_MID_INLINE
-#define SSLAPB_MID_INLINE __forceinline__
-#endif
+// Inlined, and called from the LAST branch of the kernel's regime chain.  Both were measured (tools/gpu_mid_ab.sh, same box):
+// out of line, the compiler no longer takes the warps for converged after the call and every warp collective of the code
+// that follows gets a divergence check; inlined in front of small_regime, the few-bidder loops move 17 KB down the binary —
+// either way they slow down from 1.03 to 1.10-1.16 us per round (7-12 ms at C3, more than the regime gains).
 #ifndef SSLAPB_MID_PROF
-#define SSLAPB_MID_PROF 0
+#define SSLAPB_MID_PROF 0        // profiling builds: prof[6] = 1 bidding / 2 merge / 3 compaction part of the rounds, 4 counters
 #endif
 #ifndef SSLAPB_MID_BATCH
 #define SSLAPB_MID_BATCH 4       // positions a warp keeps in flight (hot rows requested together, gathers software-pipelined)
 #endif
-#ifndef SSLAPB_KPARAM
-#define SSLAPB_KPARAM const __grid_constant__
-#endif
-static __device__ SSLAPB_MID_INLINE void mid_regime(const SslapbAuctionParams &Pk, SslapbCtrl *C, int nu, float eps_f, long long its,
+static __device__ __forceinline__ void mid_regime(const SslapbAuctionParams &Pk, SslapbCtrl *C, int nu, float eps_f, long long its,
                                                      long long max_iter, double pmin, double spread)
 {
     int done = 0;
     nu = __shfl_sync(SSLAPB_FULL, nu, 0);                      // warp-uniform for the compiler (as is `warp` below)
-    SslapbAuctionParams P;                                     // out of line: the fields used below live in registers, not
-    P.hot = Pk.hot; P.rest = Pk.rest; P.rec = Pk.rec;          // behind a load from the kernel's parameter block per use
+    SslapbAuctionParams P;                                     // the fields the rounds use (the list itself is read and written
+    P.hot = Pk.hot; P.rest = Pk.rest; P.rec = Pk.rec;          // through Pk, once each)
     P.price = Pk.price; P.cols = Pk.cols; P.vals = Pk.vals; P.rowmax = Pk.rowmax;
     __shared__ int m_li[2][SSLAPB_MID], m_dg[2][SSLAPB_MID];
     __shared__ long long m_st[2][SSLAPB_MID];
@@ -1284,8 +1288,8 @@ static __device__ SSLAPB_MID_INLINE void mid_regime(const SslapbAuctionParams &P
 #elif SSLAPB_MID_PROF == 4
         tacc += nu;                                            // (+ bids / 1e6 in the same figure)
 #endif
-        // ---- bidding: warp w sweeps positions w, w + 16, ...; SSLAPB_MID_BATCH at a time: their hot rows are requested together, and the
-        // record gather of the next position is issued before the reduction of the current one
+        // ---- bidding: warp w sweeps positions w, w + 16, ...; SSLAPB_MID_BATCH at a time: their hot rows are requested
+        // together, and the record gather of the next position is issued before the reduction of the current one
         for (int a0 = warp; a0 < nu; a0 += SSLAPB_MID_BATCH * NW) {
             SslapbHotRow row[SSLAPB_MID_BATCH];
 #pragma unroll
@@ -1823,7 +1827,7 @@ __device__ __forceinline__ void rebuild_p2o_owners(const SslapbAuctionParams &P,
 #ifdef SSLAPB_SHARDED
 #define sslapb_auction_kernel sslapb_auction_kernel_sharded   // row-sharded multi-GPU instance, see auction_sharded.cu
 #endif
-__global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(SSLAPB_KPARAM SslapbAuctionParams P)
+__global__ void __launch_bounds__(SSLAPB_THREADS, 1) sslapb_auction_kernel(const __grid_constant__ SslapbAuctionParams P)
 {
     SslapbCtrl *C = P.ctrl;
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(SSLAPB_FULL, tid >> 5, 0);
