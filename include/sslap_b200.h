@@ -99,7 +99,9 @@ size_t sslapb_meta_size(void);
 int    sslapb_abi_version(void);
 /* tuning knobs (none changes results): "t_small" (frontier size at or below which CTA 0 runs rounds alone, 0..32),
    "t_mid" (mid regime: in eps-phases whose bids the hot lists decide, CTA 0 also runs the rounds of 33..t_mid bidders alone,
-   with block barriers instead of grid barriers; 0 = off, 33..256, default 128; only in effect with t_small = 32),
+   with block barriers instead of grid barriers; 0 = off, 33..256, default 128; only in effect with t_small = 32; in a
+   row-sharded solve capped at t_shard: the ranks switch the hot form on and off independently, so only rounds that every
+   rank runs in full may depend on it),
    "watchdog_ms" (device watchdog of a single barrier wait, default 120000),
    "t_shard" (row-sharded solves: rounds with more bidders than this are split over the ranks; default 16384),
    "max_ctas" (upper bound of the persistent kernel's grid, 0 = one CTA per SM; used to co-schedule several solves on one GPU),

@@ -548,6 +548,10 @@ static int run_auction(sslapb_handle *h, const SslapbBuildFlags &F, int maximize
         CK(sslapb_launch_row_split(P.rowptr, N, h->n_ranks, h->rowsplit.as<int>(), h->stream));
         P.nranks = h->n_ranks; P.rank = h->rank; P.t_shard = h->t_shard; P.rowsplit = h->rowsplit.as<int>();
         P.xtab = h->xtab.as<unsigned long long>(); P.xcap = h->xcap; P.xround_base = h->xround;
+        // every rank switches the hot form — and with it the mid regime — on and off from the counters of its OWN rows, so the
+        // ranks may disagree about it; that is harmless only while the mid regime's rounds are rounds every rank runs in full
+        // (nu <= t_shard: no exchange).  A rank in the mid regime would never reach the exchange barrier of a sharded round.
+        if (P.t_mid > h->t_shard) P.t_mid = h->t_shard > 32 ? h->t_shard : 0;
     }
     SslapbCtrl c;
     memset(&c, 0, sizeof c);
