@@ -65,6 +65,20 @@ def test_integration_stub_matches_the_binding():
     assert f"{n_syms} `extern \"C\"` symbols" in design
 
 
+def test_every_option_is_documented():
+    """Every name sslapb_set_option accepts (csrc/api.cu) is described in the header and in INTEGRATION.md."""
+    api = open(os.path.join(ROOT, "sslap_b200", "csrc", "api.cu")).read()
+    body = api[api.index('extern "C" int sslapb_set_option'):]
+    body = body[:body.index("\n}\n")]
+    names = re.findall(r'!strcmp\(name, "([a-z0-9_]+)"\)', body)
+    assert len(names) >= 10 and "t_mid" in names and "t_small" in names
+    header = open(os.path.join(ROOT, "include", "sslap_b200.h")).read()
+    integration = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for n in names:
+        assert f'"{n}"' in header, f"option {n} is not described in include/sslap_b200.h"
+        assert f"`{n}`" in integration, f"option {n} is not described in INTEGRATION.md"
+
+
 def test_signatures_mirror_the_reference():
     # /root/reference/sslap/auction_solve.py:6-8 and check_feasible.py:5
     p = inspect.signature(sslap_b200.auction_solve).parameters
